@@ -1,0 +1,143 @@
+/*
+ * ljmd.h — C ABI of the B200-native 2-D Lennard-Jones molecular-dynamics hot path.
+ *
+ * This is the drop-in boundary for the per-step hot path of the reference script
+ *   molecular_dynamics_jax_single-host_workload.py   (cited below as MD:<line>)
+ * The reference has no FFI of its own: its "interface" is the set of Python closures
+ * defined inside main() (MD:46-131).  Every entry point below names the closure it
+ * replaces.  The reference-side binding a maintainer would add is the ctypes stub
+ * shown in INTEGRATION.md (and shipped as jax_tpus_benchmark_physics_simulation_b200/_lib.py).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types.
+ *   - all `*_dev` / R / V / F / traj / ke_pe pointers are DEVICE pointers owned by the
+ *     caller, contiguous row-major (N,2) float32 (== float2 AoS), 8-byte aligned.
+ *   - every call enqueues work on the stream given to ljmd_create() and returns
+ *     without synchronising (JAX-style async dispatch; MD:145 block_until_ready maps
+ *     to a stream synchronise done by the caller).
+ *   - inputs are never modified (the reference closures are pure); R_out/V_out may
+ *     alias R_in/V_in.
+ *   - return value 0 = success; >0 = cudaError_t; <0 = LJMD_E_* library code.
+ *     Nothing throws or aborts across the ABI.  ljmd_last_error() gives text.
+ *   - a handle is not thread-safe: one per device, driven by one host thread.
+ */
+#ifndef LJMD_H_
+#define LJMD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LJMD_ABI_VERSION 1
+
+/* library (negative) error codes */
+#define LJMD_E_INVALID   (-1)   /* bad argument                                   */
+#define LJMD_E_STATE     (-2)   /* call not valid for this handle's configuration */
+#define LJMD_E_NCCL      (-3)   /* NCCL failure (see ljmd_last_error)             */
+#define LJMD_E_NOMEM     (-4)
+#define LJMD_E_UNSUPPORTED (-5)
+
+/* force-path selection */
+#define LJMD_PATH_AUTO      0   /* all-pairs for N <= 131072, else cell list      */
+#define LJMD_PATH_ALLPAIRS  1   /* dense N x N, the reference's formulation MD:50-62 */
+#define LJMD_PATH_CELLS     2   /* sorted cell list + 3x3 stencil (requires rc)   */
+
+typedef struct ljmd_handle ljmd_t;
+
+/* Parameters captured by the reference's closures (MD:16-31). */
+typedef struct ljmd_params {
+    int64_t N;          /* particles                              MD:16          */
+    float   box;        /* fp32 box edge = sqrt(N/rho)            MD:30          */
+    float   sigma;      /* MD:26 (1.0 in the reference)                           */
+    float   epsilon;    /* MD:27 (1.0 in the reference)                           */
+    float   rc;         /* cutoff radius; INFINITY (or <=0) = none = reference    */
+    float   dt;         /* time step                              MD:19          */
+    float   skin;       /* cell-list skin (ignored by all-pairs); <=0 -> 0.3*sigma */
+    int32_t path;       /* LJMD_PATH_*                                            */
+    int32_t device;     /* CUDA device ordinal                                    */
+    void*   stream;     /* cudaStream_t (NULL = legacy default stream)            */
+} ljmd_params;
+
+int         ljmd_abi_version(void);
+const char* ljmd_last_error(void);
+
+/* closure capture of N, box_size, sigma, epsilon, dt (MD:16-31).  All scratch
+ * (partial sums, cell arrays, ping-pong state) is allocated here, never per call. */
+int  ljmd_create(ljmd_t** out, const ljmd_params* p);
+void ljmd_destroy(ljmd_t* h);
+
+/* total_energy_fn(R) -> scalar                                   MD:50-62
+ * pe_dev: device float[1].                                                        */
+int ljmd_energy(ljmd_t* h, const float* R, float* pe_dev);
+
+/* force_fn(R) -> (N,2)                                           MD:64
+ * F: device (N,2).  pe_dev may be NULL.                                           */
+int ljmd_forces(ljmd_t* h, const float* R, float* F, float* pe_dev);
+
+/* verlet_step (nsteps=1) MD:66-75, equilibrate_fn MD:77-83, production_fn MD:85-106.
+ *   sample_every > 0 and traj != NULL: after step i (0-based), if i % sample_every == 0
+ *     and i / sample_every < S (S = nsteps / sample_every) the new positions are stored in
+ *     traj[i / sample_every]  — exactly MD:88-100, including the silently dropped
+ *     out-of-range sample.  traj is (S,N,2) float32 and is fully overwritten
+ *     (rows never sampled are zero, MD:89).
+ *   energy_every > 0 and ke_pe != NULL: after step i, if i % energy_every == 0,
+ *     ke_pe[i / energy_every] = {KE, PE} of the post-step state
+ *     (KE = 0.5*sum|V|^2, PE = total_energy_fn(R)); buffer is (ceil(nsteps/energy_every),2).
+ *     Not in the reference (it never reports energies) — see DESIGN.md.
+ *   thermostat_kT > 0: velocity-rescale thermostat, V *= sqrt(kT_target / (KE/N)) after every
+ *     `thermostat_every`-th step.  Default off (<= 0) = the reference's pure NVE.
+ * No host synchronisation inside; all nsteps are enqueued in one call (MD:82,103).  */
+int ljmd_run(ljmd_t* h, const float* R_in, const float* V_in, float* R_out, float* V_out,
+             int64_t nsteps, int64_t sample_every, float* traj,
+             int64_t energy_every, float* ke_pe,
+             float thermostat_kT, int64_t thermostat_every);
+
+/* calculate_g_r histogram stage (get_histogram, MD:117-124) for S snapshots:
+ * counts[s*nbins + k] = number of unordered pairs (i<j) of snapshot s whose minimum-image
+ * distance r satisfies edges[k] <= r < edges[k+1] (last bin right-closed, values outside
+ * [edges[0], edges[nbins]] dropped — numpy/jnp.histogram semantics).  edges: device
+ * float32[nbins+1], ascending (the caller passes linspace(0, r_max, nbins+1), MD:110);
+ * counts: device int64 (S,nbins).  The normalisation (MD:111-115,126-128) is host-side
+ * arithmetic on nbins numbers.                                                     */
+int ljmd_gr_hist(ljmd_t* h, const float* R_hist, int64_t S, int32_t nbins,
+                 const float* edges, int64_t* counts);
+
+/* ---- cell-list introspection (for the bit-exact CPU recount, north_star) -------- */
+/* geometry chosen at create: cells per side, cell edge (fp32), 1/cell edge (fp32)  */
+int ljmd_cell_geometry(ljmd_t* h, int32_t* ncell_side, float* cell_size, float* inv_cell);
+/* bins R, returns per-particle cell id (device int32[N]) and per-cell counts
+ * (device int32[ncell^2]).  Either pointer may be NULL.                            */
+int ljmd_cell_assign(ljmd_t* h, const float* R, int32_t* cell_id, int32_t* cell_count);
+/* per-particle number of neighbours with minimum-image r^2 < radius^2 (j != i), found
+ * through the cell list.  nbr_count: device int32[N] in ORIGINAL particle order.     */
+int ljmd_neighbor_count(ljmd_t* h, const float* R, float radius, int32_t* nbr_count);
+/* number of cell-list rebuilds performed by the last ljmd_run (host value; syncs).   */
+int ljmd_last_rebuilds(ljmd_t* h, int64_t* rebuilds);
+
+/* ---- multi-GPU (new; the reference is single-device) ---------------------------- */
+/* One handle per rank/device.  nccl_unique_id: the 128 bytes of an ncclUniqueId made
+ * by rank 0 and broadcast by the caller (e.g. over torch.distributed/gloo).
+ * Atom decomposition for all-pairs (position all-gather each step), x-slab
+ * decomposition with halo exchange for the cell list; one all-reduce for energies.
+ * R/V arguments of ljmd_run etc. are then the FULL (N,2) arrays on every rank
+ * (replicated in, replicated out) so the Python closures keep their signatures.     */
+int ljmd_get_unique_id(void* id128);
+int ljmd_create_dist(ljmd_t** out, const ljmd_params* p, const void* nccl_unique_id,
+                     int32_t rank, int32_t nranks);
+
+/* ---- measurement helpers --------------------------------------------------------- */
+/* device time (ms) of the last ljmd_run's step loop, measured with CUDA events on the
+ * handle's stream (blocks until that run has finished).                             */
+int ljmd_last_run_ms(ljmd_t* h, float* ms);
+/* number of kernel launches issued by this handle since creation                    */
+int ljmd_launch_count(ljmd_t* h, int64_t* launches);
+/* FP32 issue-rate micro-benchmarks (FFMA / FFMA2 dependent chains): returns achieved
+ * TFLOP/s so bench.py can state the measured CUDA-core ceiling next to the nominal. */
+int ljmd_fp32_peak_probe(int32_t device, int32_t packed, float* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LJMD_H_ */

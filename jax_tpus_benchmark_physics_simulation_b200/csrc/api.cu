@@ -1,0 +1,217 @@
+// api.cu — the exported C ABI (include/ljmd.h) over the all-pairs and cell-list engines.
+#include "ljmd_internal.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+
+namespace ljmd {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+PairConsts make_pair_consts(float box, float sigma, float eps, float rc) {
+    PairConsts c{};
+    c.box = box;
+    // smallest fp32 t with fl(t / box) > 0.5  (see PairConsts in ljmd_internal.cuh)
+    volatile float t = 0.5f * box;
+    while ((float)(t / box) > 0.5f) t = nextafterf(t, 0.0f);
+    while (!((float)(t / box) > 0.5f)) t = nextafterf(t, std::numeric_limits<float>::infinity());
+    c.timg = t;
+    const bool cut = std::isfinite(rc) && rc > 0.0f;
+    c.cutoff = cut ? 1 : 0;
+    c.rc2 = cut ? rc * rc : std::numeric_limits<float>::infinity();
+    const float s2 = sigma * sigma, s6 = s2 * s2 * s2, s12 = s6 * s6;
+    c.c12 = 48.0f * eps * s12;
+    c.c6  = 24.0f * eps * s6;
+    c.d12 = 4.0f * eps * s12;
+    c.d6  = 4.0f * eps * s6;
+    return c;
+}
+
+static int create_common(ljmd_t** out, const ljmd_params* p, int rank, int nranks) {
+    if (!out || !p) { set_error("null argument"); return LJMD_E_INVALID; }
+    *out = nullptr;
+    if (p->N < 2 || p->N > (1ll << 30)) { set_error("N out of range: %lld", (long long)p->N); return LJMD_E_INVALID; }
+    if (!(p->box > 0.0f) || !std::isfinite(p->box)) { set_error("box must be positive and finite"); return LJMD_E_INVALID; }
+    if (!(p->sigma > 0.0f) || !(p->epsilon > 0.0f)) { set_error("sigma and epsilon must be positive"); return LJMD_E_INVALID; }
+    if (!std::isfinite(p->dt)) { set_error("dt must be finite"); return LJMD_E_INVALID; }
+    int ndev = 0;
+    LJ_CUDA(cudaGetDeviceCount(&ndev));
+    if (p->device < 0 || p->device >= ndev) { set_error("no CUDA device %d (found %d)", p->device, ndev); return LJMD_E_INVALID; }
+    LJ_CUDA(cudaSetDevice(p->device));
+    cudaDeviceProp prop;
+    LJ_CUDA(cudaGetDeviceProperties(&prop, p->device));
+    if (prop.major != 10) {
+        set_error("ljmd is built for sm_100a (B200) only; device %d is sm_%d%d", p->device, prop.major, prop.minor);
+        return LJMD_E_UNSUPPORTED;
+    }
+    ljmd_handle* h = new ljmd_handle();
+    memset(h, 0, sizeof(*h));
+    h->p = *p;
+    if (!(h->p.skin > 0.0f)) h->p.skin = 0.3f * p->sigma;
+    h->pc = make_pair_consts(p->box, p->sigma, p->epsilon, p->rc);
+    h->stream = (cudaStream_t)p->stream;
+    h->num_sms = prop.multiProcessorCount;
+    h->rank = rank;
+    h->nranks = nranks;
+    h->timed = true;
+    int path = p->path;
+    if (path == LJMD_PATH_AUTO) path = (p->N <= 131072 || !h->pc.cutoff) ? LJMD_PATH_ALLPAIRS : LJMD_PATH_CELLS;
+    if (path == LJMD_PATH_CELLS && !h->pc.cutoff) {
+        set_error("the cell-list path needs a finite cutoff rc");
+        delete h;
+        return LJMD_E_INVALID;
+    }
+    if (path != LJMD_PATH_ALLPAIRS && path != LJMD_PATH_CELLS) { set_error("bad path %d", path); delete h; return LJMD_E_INVALID; }
+    h->path = path;
+    int rcode = 0;
+    if ((rcode = (int)cudaEventCreate(&h->ev0)) || (rcode = (int)cudaEventCreate(&h->ev1))) {
+        set_error("cudaEventCreate failed");
+        delete h;
+        return rcode;
+    }
+    // the all-pairs engine is always present: it also serves ljmd_gr_hist and small-N fallbacks
+    rcode = (path == LJMD_PATH_ALLPAIRS) ? ap_create(h) : cells_create(h);
+    if (rcode) { ljmd_destroy(h); return rcode; }
+    *out = h;
+    return 0;
+}
+
+}  // namespace ljmd
+
+using namespace ljmd;
+
+extern "C" {
+
+int ljmd_abi_version(void) { return LJMD_ABI_VERSION; }
+const char* ljmd_last_error(void) { return g_err; }
+
+int ljmd_create(ljmd_t** out, const ljmd_params* p) { return create_common(out, p, 0, 1); }
+
+void ljmd_destroy(ljmd_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->p.device);
+    cudaStreamSynchronize(h->stream);
+    ap_destroy(h);
+    cells_destroy(h);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+}
+
+static int run_dispatch(ljmd_t* h, const float* R_in, const float* V_in, float* R_out, float* V_out,
+                        float* F_out, float* pe_out, const RunCtl& rc) {
+    LJ_CUDA(cudaSetDevice(h->p.device));
+    const float2* R = reinterpret_cast<const float2*>(R_in);
+    const float2* V = reinterpret_cast<const float2*>(V_in);
+    if (h->path == LJMD_PATH_ALLPAIRS)
+        return ap_run(h, R, V, reinterpret_cast<float2*>(R_out), reinterpret_cast<float2*>(V_out),
+                      reinterpret_cast<float2*>(F_out), pe_out, rc);
+    return cells_run(h, R, V, reinterpret_cast<float2*>(R_out), reinterpret_cast<float2*>(V_out),
+                     reinterpret_cast<float2*>(F_out), pe_out, rc);
+}
+
+int ljmd_energy(ljmd_t* h, const float* R, float* pe_dev) {
+    if (!h || !R || !pe_dev) { set_error("null argument"); return LJMD_E_INVALID; }
+    RunCtl rc{};
+    return run_dispatch(h, R, nullptr, nullptr, nullptr, nullptr, pe_dev, rc);
+}
+
+int ljmd_forces(ljmd_t* h, const float* R, float* F, float* pe_dev) {
+    if (!h || !R || !F) { set_error("null argument"); return LJMD_E_INVALID; }
+    RunCtl rc{};
+    return run_dispatch(h, R, nullptr, nullptr, nullptr, F, pe_dev, rc);
+}
+
+int ljmd_run(ljmd_t* h, const float* R_in, const float* V_in, float* R_out, float* V_out,
+             int64_t nsteps, int64_t sample_every, float* traj, int64_t energy_every, float* ke_pe,
+             float thermostat_kT, int64_t thermostat_every) {
+    if (!h || !R_in || !V_in || !R_out || !V_out) { set_error("null argument"); return LJMD_E_INVALID; }
+    if (nsteps < 0 || sample_every < 0 || energy_every < 0 || thermostat_every < 0) {
+        set_error("negative step count");
+        return LJMD_E_INVALID;
+    }
+    const size_t bytes = sizeof(float) * 2 * (size_t)h->p.N;
+    if (nsteps == 0) {   // fori_loop(0, 0, ...) returns the initial state (MD:82)
+        LJ_CUDA(cudaSetDevice(h->p.device));
+        if (R_out != R_in) LJ_CUDA(cudaMemcpyAsync(R_out, R_in, bytes, cudaMemcpyDeviceToDevice, h->stream));
+        if (V_out != V_in) LJ_CUDA(cudaMemcpyAsync(V_out, V_in, bytes, cudaMemcpyDeviceToDevice, h->stream));
+        return 0;
+    }
+    RunCtl rc{};
+    rc.nsteps = nsteps;
+    rc.sample_every = (traj && sample_every > 0) ? sample_every : 0;
+    rc.S = rc.sample_every ? nsteps / rc.sample_every : 0;
+    if (rc.S == 0) rc.sample_every = 0;
+    rc.traj = reinterpret_cast<float2*>(traj);
+    rc.energy_every = (ke_pe && energy_every > 0) ? energy_every : 0;
+    rc.ke_pe = ke_pe;
+    rc.thermo_kT = (thermostat_kT > 0.0f && thermostat_every > 0) ? thermostat_kT : 0.0f;
+    rc.thermo_every = rc.thermo_kT > 0.0f ? thermostat_every : 0;
+    return run_dispatch(h, R_in, V_in, R_out, V_out, nullptr, nullptr, rc);
+}
+
+int ljmd_gr_hist(ljmd_t* h, const float* R_hist, int64_t S, int32_t nbins, const float* edges,
+                 int64_t* counts) {
+    if (!h || !counts || !edges || (S > 0 && !R_hist) || S < 0) { set_error("bad argument"); return LJMD_E_INVALID; }
+    LJ_CUDA(cudaSetDevice(h->p.device));
+    return ap_gr_hist(h, reinterpret_cast<const float2*>(R_hist), S, nbins, edges,
+                      reinterpret_cast<long long*>(counts));
+}
+
+int ljmd_cell_geometry(ljmd_t* h, int32_t* ncell_side, float* cell_size, float* inv_cell) {
+    if (!h) { set_error("null handle"); return LJMD_E_INVALID; }
+    if (h->path != LJMD_PATH_CELLS) { set_error("handle is not on the cell-list path"); return LJMD_E_STATE; }
+    return cells_geometry(h, ncell_side, cell_size, inv_cell);
+}
+
+int ljmd_cell_assign(ljmd_t* h, const float* R, int32_t* cell_id, int32_t* cell_count) {
+    if (!h || !R) { set_error("null argument"); return LJMD_E_INVALID; }
+    if (h->path != LJMD_PATH_CELLS) { set_error("handle is not on the cell-list path"); return LJMD_E_STATE; }
+    LJ_CUDA(cudaSetDevice(h->p.device));
+    return cells_assign(h, reinterpret_cast<const float2*>(R), cell_id, cell_count);
+}
+
+int ljmd_neighbor_count(ljmd_t* h, const float* R, float radius, int32_t* nbr_count) {
+    if (!h || !R || !nbr_count) { set_error("null argument"); return LJMD_E_INVALID; }
+    if (h->path != LJMD_PATH_CELLS) { set_error("handle is not on the cell-list path"); return LJMD_E_STATE; }
+    LJ_CUDA(cudaSetDevice(h->p.device));
+    return cells_neighbor_count(h, reinterpret_cast<const float2*>(R), radius, nbr_count);
+}
+
+int ljmd_last_rebuilds(ljmd_t* h, int64_t* rebuilds) {
+    if (!h || !rebuilds) { set_error("null argument"); return LJMD_E_INVALID; }
+    if (h->path != LJMD_PATH_CELLS) { *rebuilds = 0; return 0; }
+    LJ_CUDA(cudaSetDevice(h->p.device));
+    *rebuilds = cells_last_rebuilds(h);
+    return 0;
+}
+
+int ljmd_last_run_ms(ljmd_t* h, float* ms) {
+    if (!h || !ms) { set_error("null argument"); return LJMD_E_INVALID; }
+    LJ_CUDA(cudaSetDevice(h->p.device));
+    LJ_CUDA(cudaEventSynchronize(h->ev1));
+    LJ_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return 0;
+}
+
+int ljmd_launch_count(ljmd_t* h, int64_t* launches) {
+    if (!h || !launches) { set_error("null argument"); return LJMD_E_INVALID; }
+    *launches = h->launches;
+    return 0;
+}
+
+int ljmd_fp32_peak_probe(int32_t device, int32_t packed, float* tflops) {
+    if (!tflops) { set_error("null argument"); return LJMD_E_INVALID; }
+    return fp32_peak_probe(device, packed, tflops);
+}
+
+}  // extern "C"

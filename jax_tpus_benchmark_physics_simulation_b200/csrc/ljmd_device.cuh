@@ -1,0 +1,116 @@
+// ljmd_device.cuh — device-side building blocks shared by the all-pairs and cell-list kernels.
+#pragma once
+#include "ljmd_internal.cuh"
+
+namespace ljmd {
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // MUFU.RCP, <= 1 ulp
+    return r;
+}
+
+// minimum image, bit-identical to  d - box * round(d / box)  of MD:46-48 for |d| <= box
+// (see PairConsts::timg).  FSETP + LOP3 + predicated FADD.
+__device__ __forceinline__ float min_image(float d, float box, float timg) {
+    return (fabsf(d) >= timg) ? __fsub_rn(d, copysignf(box, d)) : d;
+}
+
+// One ordered pair (i <- j) of total_energy_fn / force_fn (MD:50-64):
+//   r2 = dx^2 + dy^2 with each operation rounded once (no FMA contraction), so the pair set
+//   {r2 < rc2} is decided on the same fp32 r2 as the CPU restatement;
+//   ir2 = 1/r2 (MUFU.RCP); force scalar and pair energy in the sigma/epsilon-folded form.
+// KEEPTEST: an additional "j is not i" predicate is applied (diagonal mask MD:54-55,60).
+template <bool CUTOFF, bool PE, bool KEEPTEST>
+__device__ __forceinline__ void pair_accum(float xi, float yi, float xj, float yj, bool keep,
+                                           const PairConsts& c, float& fx, float& fy, float& pe) {
+    float dx = min_image(__fsub_rn(xi, xj), c.box, c.timg);
+    float dy = min_image(__fsub_rn(yi, yj), c.box, c.timg);
+    float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    float ir2 = rcp_approx(r2);
+    if (CUTOFF) {
+        bool in = r2 < c.rc2;
+        if (KEEPTEST) in = in && keep;
+        ir2 = in ? ir2 : 0.0f;
+    } else if (KEEPTEST) {
+        ir2 = keep ? ir2 : 0.0f;
+    }
+    float ir6 = ir2 * ir2 * ir2;
+    float f = fmaf(ir6, c.c12, -c.c6) * (ir6 * ir2);
+    fx = fmaf(f, dx, fx);
+    fy = fmaf(f, dy, fy);
+    if (PE) pe = fmaf(ir6, fmaf(ir6, c.d12, -c.d6), pe);
+}
+
+// jnp.mod(x, box) of MD:72 (result has the divisor's sign; can return exactly `box` for tiny
+// negative x).  Fast exact paths for the ranges a step can produce, generic fmodf otherwise.
+__device__ __forceinline__ float wrap_box(float x, float box) {
+    if (x >= 0.0f && x < box) return x + 0.0f;                 // (+0.0f maps -0 to +0 like copysign(0, box))
+    if (x >= box && x < 2.0f * box) return __fsub_rn(x, box);  // exact (fmod is exact)
+    if (x < 0.0f && x > -box) return __fadd_rn(x, box);        // fmod(x) = x, then + box (one rounding)
+    float m = fmodf(x, box);
+    if (m != 0.0f) { if (m < 0.0f) m = __fadd_rn(m, box); } else m = 0.0f;
+    return m;
+}
+
+// velocity-Verlet pieces with the reference's rounding sequence (MD:70-74):
+//   V_half = V + (0.5*F)*dt      R_new = mod(R + V_half*dt, box)
+__device__ __forceinline__ float kick(float v, float f, float dt) {
+    return __fadd_rn(v, __fmul_rn(__fmul_rn(0.5f, f), dt));
+}
+__device__ __forceinline__ float drift(float r, float vh, float dt, float box) {
+    return wrap_box(__fadd_rn(r, __fmul_rn(vh, dt)), box);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum (deterministic: fixed shuffle tree + fixed warp order); result valid in thread 0.
+template <int THREADS>
+__device__ __forceinline__ float block_sum(float v, float* smem /* THREADS/32 floats */) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) smem[w] = v;
+    __syncthreads();
+    float t = 0.0f;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < THREADS / 32; ++k) t += smem[k];
+    }
+    return t;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Grid-wide barrier for a cooperative (co-resident) launch: monotone arrival counter in L2.
+// `target` = number of arrivals that completes this barrier (epoch * gridDim.x).
+// A spin that lasts longer than ~2^32 clocks (about 2 s) raises *err and falls through, so a
+// lost rank can never hang the GPU.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target, int* err) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        long long t0 = clock64();
+        while (ld_acquire_gpu(counter) < target) {
+            if (clock64() - t0 > (1ll << 32)) { atomicExch(err, 1); break; }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+}  // namespace ljmd
