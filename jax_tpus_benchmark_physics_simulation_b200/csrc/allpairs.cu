@@ -29,14 +29,22 @@ namespace ljmd {
 namespace {
 
 constexpr int AP_THREADS = 128;   // 4 warps: one per SM sub-partition
+#ifndef AP_UNROLL
+#define AP_UNROLL 8
+#endif
+#ifndef AP_MINBLOCKS
+#define AP_MINBLOCKS 4
+#endif
+constexpr int kApUnroll = AP_UNROLL;   // j particles per unrolled inner-loop body
 constexpr int J_UNIT     = 8;     // granularity of the j split (particles)
-constexpr int TILE_J     = 512;   // j particles staged per shared-memory tile (4 KB)
+constexpr int TILE_J     = 512;   // j particles staged per shared-memory tile (8 KB)
+constexpr int RED_LANES  = 8;     // lanes that cooperate on one particle's partial sum
 constexpr float SENT_J   = 1.0e18f;    // padding particles: far away, contribute exactly 0
 constexpr float SENT_I   = -1.0e18f;
 
 struct ApArgs {
     PairConsts pc;
-    int   N, G, NJu, nI, maxseg;
+    int   N, G, NJu, nI, maxseg, ppc;   // ppc = particles owned per CTA in phase [d]
     float dt;
     const long long* cta_start;   // [G+1] flat (i-block * NJu + j-unit) range owned by each CTA
     const int*       cta_ib0;     // [G]   first i-block a CTA touches
@@ -51,6 +59,7 @@ struct ApArgs {
     float*           ke_part;     // [2*G]
     unsigned*        bar;
     int*             err;
+    long long*       prof;        // optional [G][4] phase clocks (debug: LJMD_AP_PROF=1)
     long long        s_begin, s_end;   // steps [s_begin, s_end); s = -1 is the prologue force
     RunCtl           rc;
     float2*          R_out;
@@ -60,6 +69,8 @@ struct ApArgs {
 };
 
 // ---- phase [b]: one segment = (i-block ib) x (j units [ju0, ju0+julen)) ---------------------
+// Shared-memory tile layout: one float4 per j particle = (-xj, -xj, -yj, -yj): a single
+// broadcast LDS.128 feeds the packed (two i per thread) pair evaluation.
 template <int IPT, bool CUTOFF, bool PE>
 __device__ __forceinline__ void ap_segment(const ApArgs& a, const float2* __restrict__ Rcur,
                                            int ib, int ju0, int julen, float4* sj,
@@ -67,13 +78,16 @@ __device__ __forceinline__ void ap_segment(const ApArgs& a, const float2* __rest
     constexpr int BI = AP_THREADS * IPT;
     const int tid = threadIdx.x;
     const PairConsts pc = a.pc;
+    const PairConsts2 pc2 = make_pair_consts2(pc);
     float xi[IPT], yi[IPT];
     int   ii[IPT];
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
         ii[k] = ib * BI + k * AP_THREADS + tid;
-        if (ii[k] < a.N) { float2 r = __ldcg(&Rcur[ii[k]]); xi[k] = r.x; yi[k] = r.y; }
-        else             { xi[k] = SENT_I; yi[k] = SENT_I; }
+        if (ii[k] < a.N) {
+            const float* rp = reinterpret_cast<const float*>(Rcur + ii[k]);
+            xi[k] = ldcg_f32(rp); yi[k] = ldcg_f32(rp + 1);
+        } else { xi[k] = SENT_I; yi[k] = SENT_I; }
         fx[k] = 0.0f; fy[k] = 0.0f;
     }
     const int j0 = ju0 * J_UNIT, jend = (ju0 + julen) * J_UNIT;
@@ -85,39 +99,60 @@ __device__ __forceinline__ void ap_segment(const ApArgs& a, const float2* __rest
         for (int q = tid; q < cnt; q += AP_THREADS) {
             const int j = jt + q;
             float2 r = (j < a.N) ? __ldcg(&Rcur[j]) : make_float2(SENT_J, SENT_J);
-            reinterpret_cast<float2*>(sj)[q] = r;
+            sj[q] = make_float4(-r.x, -r.x, -r.y, -r.y);
         }
         __syncthreads();
-        float tfx[IPT], tfy[IPT], tpe[IPT];               // per-tile sums (bounded chain length)
-#pragma unroll
-        for (int k = 0; k < IPT; ++k) { tfx[k] = 0.0f; tfy[k] = 0.0f; tpe[k] = 0.0f; }
-        const bool diag = (jt < i_hi) && (jt + cnt > i_lo);   // tile contains some i == j
-        if (!diag) {
-#pragma unroll 4
-            for (int q = 0; q < cnt / 2; ++q) {
-                const float4 v = sj[q];                    // two j particles, warp broadcast
-#pragma unroll
-                for (int k = 0; k < IPT; ++k) {
-                    pair_accum<CUTOFF, PE, false>(xi[k], yi[k], v.x, v.y, true, pc, tfx[k], tfy[k], tpe[k]);
-                    pair_accum<CUTOFF, PE, false>(xi[k], yi[k], v.z, v.w, true, pc, tfx[k], tfy[k], tpe[k]);
+        // the only j that can equal one of this CTA's i lie in [i_lo, i_hi): split the tile into
+        // (before | diagonal | after) so the index test is paid on the overlap only
+        const int qd0 = min(max(i_lo - jt, 0), cnt), qd1 = min(max(i_hi - jt, 0), cnt);
+        if constexpr (IPT == 2) {
+            const float2 xi2 = make_float2(xi[0], xi[1]), yi2 = make_float2(yi[0], yi[1]);
+            float2 tfx = make_float2(0.0f, 0.0f), tfy = tfx, tpe = tfx;   // per-tile sums
+#pragma unroll 1
+            for (int part = 0; part < 3; ++part) {
+                const int qa = (part == 0) ? 0 : (part == 1 ? qd0 : qd1);
+                const int qb = (part == 0) ? qd0 : (part == 1 ? qd1 : cnt);
+                if (part != 1) {
+#pragma unroll kApUnroll
+                    for (int q = qa; q < qb; ++q) {
+                        const float4 v = sj[q];            // one j particle, warp broadcast
+                        pair2_accum<CUTOFF, PE, false>(xi2, yi2, make_float2(v.x, v.y), make_float2(v.z, v.w),
+                                                       true, true, pc, pc2, tfx, tfy, tpe);
+                    }
+                } else {
+#pragma unroll kApUnroll
+                    for (int q = qa; q < qb; ++q) {
+                        const float4 v = sj[q];
+                        const int j = jt + q;
+                        pair2_accum<CUTOFF, PE, true>(xi2, yi2, make_float2(v.x, v.y), make_float2(v.z, v.w),
+                                                      j != ii[0], j != ii[1], pc, pc2, tfx, tfy, tpe);
+                    }
                 }
             }
+            fx[0] += tfx.x; fx[1] += tfx.y; fy[0] += tfy.x; fy[1] += tfy.y;
+            if (PE) pe_acc += tpe.x + tpe.y;
         } else {
-#pragma unroll 2
-            for (int q = 0; q < cnt / 2; ++q) {
-                const float4 v = sj[q];
-                const int j = jt + 2 * q;
-#pragma unroll
-                for (int k = 0; k < IPT; ++k) {
-                    pair_accum<CUTOFF, PE, true>(xi[k], yi[k], v.x, v.y, j != ii[k], pc, tfx[k], tfy[k], tpe[k]);
-                    pair_accum<CUTOFF, PE, true>(xi[k], yi[k], v.z, v.w, (j + 1) != ii[k], pc, tfx[k], tfy[k], tpe[k]);
+            float tfx = 0.0f, tfy = 0.0f, tpe = 0.0f;
+#pragma unroll 1
+            for (int part = 0; part < 3; ++part) {
+                const int qa = (part == 0) ? 0 : (part == 1 ? qd0 : qd1);
+                const int qb = (part == 0) ? qd0 : (part == 1 ? qd1 : cnt);
+                if (part != 1) {
+#pragma unroll kApUnroll
+                    for (int q = qa; q < qb; ++q) {
+                        const float4 v = sj[q];
+                        pair_accum<CUTOFF, PE, false>(xi[0], yi[0], -v.x, -v.z, true, pc, tfx, tfy, tpe);
+                    }
+                } else {
+#pragma unroll kApUnroll
+                    for (int q = qa; q < qb; ++q) {
+                        const float4 v = sj[q];
+                        pair_accum<CUTOFF, PE, true>(xi[0], yi[0], -v.x, -v.z, (jt + q) != ii[0], pc, tfx, tfy, tpe);
+                    }
                 }
             }
-        }
-#pragma unroll
-        for (int k = 0; k < IPT; ++k) {
-            fx[k] += tfx[k]; fy[k] += tfy[k];
-            if (PE) pe_acc += tpe[k];
+            fx[0] += tfx; fy[0] += tfy;
+            if (PE) pe_acc += tpe;
         }
     }
 }
@@ -157,15 +192,18 @@ __device__ __forceinline__ double warp_sum_array(const float* p, int n) {
 }
 
 template <int IPT, bool CUTOFF>
-__global__ void __launch_bounds__(AP_THREADS)
+__global__ void __launch_bounds__(AP_THREADS, AP_MINBLOCKS)
 ap_persistent_kernel(const ApArgs a) {
     constexpr int BI = AP_THREADS * IPT;
-    __shared__ float4 sj[TILE_J / 2];
+    __shared__ float4 sj[TILE_J];
     __shared__ float  sred[AP_THREADS / 32];
     __shared__ float  s_lambda;
     const int c = blockIdx.x, tid = threadIdx.x;
     const RunCtl rc = a.rc;
     unsigned epoch = 0;
+    __shared__ long long pt[5];                              // debug phase clocks (thread 0 only)
+    const bool prof = (a.prof != nullptr) && tid == 0;
+    if (prof) { pt[0] = pt[1] = pt[2] = pt[3] = 0; }
 
     for (long long s = a.s_begin; s < a.s_end; ++s) {
         const float2* Rcur  = (s < 0) ? a.R_in : ((s & 1) ? a.Rbuf1 : a.Rbuf0);
@@ -180,25 +218,46 @@ ap_persistent_kernel(const ApArgs a) {
         const bool sample  = kick1 && rc.sample_every > 0 && (s % rc.sample_every == 0) &&
                              (s / rc.sample_every < rc.S);   // MD:93-100
 
+        if (prof) pt[4] = clock64();
         // ---- [b] partial forces of R_cur ------------------------------------------------------
         if (want_pe) ap_phase_forces<IPT, CUTOFF, true >(a, Rcur, sj, sred, par);
         else         ap_phase_forces<IPT, CUTOFF, false>(a, Rcur, sj, sred, par);
+        if (prof) { long long t = clock64(); pt[0] += t - pt[4]; pt[4] = t; }
         grid_barrier(a.bar, (++epoch) * (unsigned)a.G, a.err);
+        if (prof) { long long t = clock64(); pt[1] += t - pt[4]; pt[4] = t; }
 
         // ---- [d] reduce partials, finish the velocity-Verlet step -----------------------------
+        // CTA c owns particles [c*ppc, (c+1)*ppc); a group of RED_LANES lanes sums the partials of
+        // one particle (strided over the contributing CTAs, then a fixed xor-shuffle tree), and
+        // lane 0 of the group integrates it.  Fixed order => bit-reproducible, no atomics.
         float ke_thread = 0.0f;
-        for (int g = c * AP_THREADS + tid; g < a.N; g += a.G * AP_THREADS) {
-            const int ib = g / BI, il = g - ib * BI;
-            const int2 cc = a.iblk_ctas[ib];
+        const int grp = tid / RED_LANES, gl = tid % RED_LANES;
+        const int g_end = min(a.N, (c + 1) * a.ppc);
+        for (int gb = c * a.ppc; gb < g_end; gb += AP_THREADS / RED_LANES) {   // block-uniform trip count
+            const int g = gb + grp;
+            const bool live = g < g_end;
             float Fx = 0.0f, Fy = 0.0f;
-#pragma unroll 4
-            for (int c2 = cc.x; c2 <= cc.y; ++c2) {
-                const int seg = ib - a.cta_ib0[c2];
-                const float2 p = __ldcg(&a.part[((size_t)c2 * a.maxseg + seg) * BI + il]);
-                Fx += p.x; Fy += p.y;
+            float2 r = make_float2(0.0f, 0.0f), v = make_float2(0.0f, 0.0f);
+            if (live && gl == 0) {                          // issued early: overlaps the partial loads
+                r = __ldcg(&Rcur[g]);
+                if (rc.nsteps > 0) v = a.Vh[g];
             }
-            const float2 r = __ldcg(&Rcur[g]);
-            float2 v = (rc.nsteps > 0) ? a.Vh[g] : make_float2(0.0f, 0.0f);
+            if (live) {
+                const int ib = g / BI, il = g - ib * BI;
+                const int2 cc = a.iblk_ctas[ib];
+#pragma unroll 4
+                for (int c2 = cc.x + gl; c2 <= cc.y; c2 += RED_LANES) {
+                    const int seg = ib - a.cta_ib0[c2];
+                    const float2 p = __ldcg(&a.part[((size_t)c2 * a.maxseg + seg) * BI + il]);
+                    Fx += p.x; Fy += p.y;
+                }
+            }
+#pragma unroll
+            for (int o = RED_LANES / 2; o > 0; o >>= 1) {
+                Fx += __shfl_xor_sync(0xffffffffu, Fx, o);
+                Fy += __shfl_xor_sync(0xffffffffu, Fy, o);
+            }
+            if (!live || gl != 0) continue;
             if (kick1) { v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt); }   // MD:74
             if (want_e || thermo) ke_thread += v.x * v.x + v.y * v.y;
             if (sample) rc.traj[(size_t)(s / rc.sample_every) * a.N + g] = r;
@@ -234,7 +293,7 @@ ap_persistent_kernel(const ApArgs a) {
             }
             __syncthreads();
             const float lam = s_lambda;
-            for (int g = c * AP_THREADS + tid; g < a.N; g += a.G * AP_THREADS) {
+            for (int g = c * a.ppc + tid; g < g_end; g += AP_THREADS) {
                 const float2 r = __ldcg(&Rcur[g]);
                 const float2 F = a.Ftmp[g];
                 float2 v = a.Vh[g];
@@ -251,7 +310,9 @@ ap_persistent_kernel(const ApArgs a) {
                 }
             }
         }
+        if (prof) { long long t = clock64(); pt[2] += t - pt[4]; pt[4] = t; }
         grid_barrier(a.bar, (++epoch) * (unsigned)a.G, a.err);
+        if (prof) { long long t = clock64(); pt[3] += t - pt[4]; pt[4] = t; }
 
         // ---- energies of the post-step state (one warp, fixed order, double combine) ----------
         if (c == 0 && tid < 32 && want_pe) {
@@ -267,6 +328,10 @@ ap_persistent_kernel(const ApArgs a) {
                 }
             }
         }
+    }
+    if (prof) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a.prof[c * 4 + k] = pt[k];
     }
 }
 
@@ -288,9 +353,9 @@ gr_hist_kernel(const float2* __restrict__ Rh, int N, float box, float timg, int 
                int ntile) {
     // blockIdx.x -> (tile_i <= tile_j) upper-triangular tile pair; blockIdx.y -> snapshot
     extern __shared__ unsigned char smem_raw[];
-    float*    sedges = reinterpret_cast<float*>(smem_raw);                  // nbins+1
+    float2*   sj     = reinterpret_cast<float2*>(smem_raw);                 // GR_TILE (8-byte aligned)
+    float*    sedges = reinterpret_cast<float*>(sj + GR_TILE);              // nbins+1
     unsigned* shist  = reinterpret_cast<unsigned*>(sedges + nbins + 1);     // nbins
-    float2*   sj     = reinterpret_cast<float2*>(shist + nbins);            // GR_TILE
     const int tid = threadIdx.x;
     int t = blockIdx.x, ti = 0;
     while (t >= ntile - ti) { t -= ntile - ti; ++ti; }
@@ -340,6 +405,7 @@ struct AllPairs {
     float *pe_part = nullptr, *ke_part = nullptr;
     unsigned* bar = nullptr;
     int* err = nullptr;
+    long long* prof = nullptr;
     ApKernel kernel = nullptr;
 };
 
@@ -363,14 +429,39 @@ int ap_create(ljmd_handle* h) {
     const long long W = (long long)ap->nI * ap->NJu;
     // at least ~64 j per thread per CTA so tiny systems do not pay for a wide barrier
     long long g_work = std::max<long long>(1, W / (64 / J_UNIT));
-    long long g_own  = (N + AP_THREADS - 1) / AP_THREADS;       // enough threads to own particles once
-    (void)g_own;
     ap->G = (int)std::min<long long>((long long)per_sm * h->num_sms, std::min(g_work, W));
     if (const char* e = getenv("LJMD_AP_GRID")) ap->G = std::max(1, std::min(atoi(e), ap->G));
 
-    // stream-K split of the flattened (i-block, j-unit) space
+    // stream-K split of the flattened (i-block, j-unit) space, by COST: a j unit that overlaps
+    // its own i-block runs the index-tested loop (~16% more instructions), so it weighs more.
+    const long long W_PLAIN = 100, W_DIAG = (ap->ipt == 2) ? 116 : 110;
+    const int du = BI / J_UNIT;                       // diagonal units per row
+    auto row_cost = [&](int b, long long u) {         // cost of units [0, u) of row b
+        const long long d0 = std::min<long long>((long long)b * du, ap->NJu);
+        const long long d1 = std::min<long long>(d0 + du, ap->NJu);
+        const long long nd = std::max<long long>(0, std::min(u, d1) - d0);
+        return u * W_PLAIN + nd * (W_DIAG - W_PLAIN);
+    };
+    std::vector<long long> rowsum(ap->nI + 1, 0);
+    for (int b = 0; b < ap->nI; ++b) rowsum[b + 1] = rowsum[b] + row_cost(b, ap->NJu);
+    const long long total_cost = rowsum[ap->nI];
     std::vector<long long> start(ap->G + 1);
-    for (int c = 0; c <= ap->G; ++c) start[c] = (long long)(((__int128)W * c) / ap->G);
+    {
+        int b = 0;
+        for (int c = 0; c <= ap->G; ++c) {
+            const long long target = (long long)(((__int128)total_cost * c) / ap->G);
+            while (b + 1 < ap->nI && rowsum[b + 1] <= target) ++b;
+            long long lo = 0, hi = ap->NJu;          // smallest u with rowsum[b] + row_cost(b,u) >= target
+            while (lo < hi) {
+                const long long mid = (lo + hi) / 2;
+                if (rowsum[b] + row_cost(b, mid) >= target) hi = mid; else lo = mid + 1;
+            }
+            start[c] = (long long)b * ap->NJu + lo;
+        }
+        start[0] = 0;
+        start[ap->G] = W;
+        for (int c = 1; c <= ap->G; ++c) start[c] = std::max(start[c], start[c - 1]);
+    }
     std::vector<int> ib0(ap->G);
     int maxseg = 1;
     for (int c = 0; c < ap->G; ++c) {
@@ -406,6 +497,7 @@ int ap_create(ljmd_handle* h) {
     LJ_CUDA(cudaMalloc(&ap->bar, sizeof(unsigned)));
     LJ_CUDA(cudaMalloc(&ap->err, sizeof(int)));
     LJ_CUDA(cudaMemset(ap->err, 0, sizeof(int)));
+    if (getenv("LJMD_AP_PROF")) LJ_CUDA(cudaMalloc(&ap->prof, sizeof(long long) * 4 * ap->G));
     return 0;
 }
 
@@ -432,12 +524,13 @@ int ap_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_out
     }
     ApArgs a{};
     a.pc = h->pc;
+    a.ppc = (int)((N + ap->G - 1) / ap->G);
     a.N = (int)N; a.G = ap->G; a.NJu = ap->NJu; a.nI = ap->nI; a.maxseg = ap->maxseg;
     a.dt = h->p.dt;
     a.cta_start = ap->d_cta_start; a.cta_ib0 = ap->d_cta_ib0; a.iblk_ctas = ap->d_iblk;
     a.R_in = R_in; a.Rbuf0 = ap->Rbuf0; a.Rbuf1 = ap->Rbuf1; a.Vh = ap->Vh; a.Ftmp = ap->Ftmp;
     a.part = ap->part; a.pe_part = ap->pe_part; a.ke_part = ap->ke_part;
-    a.bar = ap->bar; a.err = ap->err;
+    a.bar = ap->bar; a.err = ap->err; a.prof = ap->prof;
     a.rc = rc;
     a.R_out = R_out; a.V_out = V_out; a.F_out = F_out; a.pe_out = pe_out;
 
@@ -459,6 +552,36 @@ int ap_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_out
         s = e;
     }
     if (h->timed) LJ_CUDA(cudaEventRecord(h->ev1, st));
+    if (ap->prof) {   // debug: mean / max clocks per phase per step of the last launch
+        LJ_CUDA(cudaStreamSynchronize(st));
+        std::vector<long long> pv(4 * ap->G);
+        LJ_CUDA(cudaMemcpy(pv.data(), ap->prof, sizeof(long long) * pv.size(), cudaMemcpyDeviceToHost));
+        const double nst = (double)std::max<long long>(1, a.s_end - a.s_begin);
+        const char* nm[4] = {"forces", "barrierA", "integrate", "barrierB"};
+        for (int k = 0; k < 4; ++k) {
+            double mean = 0, mx = 0;
+            for (int c = 0; c < ap->G; ++c) { mean += pv[c * 4 + k]; mx = std::max<double>(mx, (double)pv[c * 4 + k]); }
+            fprintf(stderr, "[ljmd prof] %-10s mean %9.0f  max %9.0f clocks/step (G=%d)\n", nm[k],
+                    mean / ap->G / nst, mx / nst, ap->G);
+        }
+        if (getenv("LJMD_AP_PROF_CTAS")) {
+            fprintf(stderr, "[ljmd prof] forces clocks/step by CTA:");
+            for (int c = 0; c < ap->G; ++c) fprintf(stderr, "%s%d:%.0f", (c % 16) ? " " : "\n  ", c, pv[c * 4] / nst);
+            fprintf(stderr, "\n");
+        }
+    }
+    return 0;
+}
+
+int ap_check_error(ljmd_handle* h) {
+    AllPairs* ap = h->ap;
+    if (!ap) return 0;
+    int e = 0;
+    LJ_CUDA(cudaMemcpy(&e, ap->err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e) {
+        set_error("all-pairs persistent kernel: grid barrier timed out (device error flag %d)", e);
+        return LJMD_E_STATE;
+    }
     return 0;
 }
 

@@ -33,6 +33,7 @@ PairConsts make_pair_consts(float box, float sigma, float eps, float rc) {
     c.c6  = 24.0f * eps * s6;
     c.d12 = 4.0f * eps * s12;
     c.d6  = 4.0f * eps * s6;
+    c.one = 1.0f;
     return c;
 }
 
@@ -200,7 +201,7 @@ int ljmd_last_run_ms(ljmd_t* h, float* ms) {
     LJ_CUDA(cudaSetDevice(h->p.device));
     LJ_CUDA(cudaEventSynchronize(h->ev1));
     LJ_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
-    return 0;
+    return ap_check_error(h);
 }
 
 int ljmd_launch_count(ljmd_t* h, int64_t* launches) {

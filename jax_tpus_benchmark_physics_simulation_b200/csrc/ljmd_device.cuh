@@ -29,8 +29,7 @@ __device__ __forceinline__ void pair_accum(float xi, float yi, float xj, float y
     float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
     float ir2 = rcp_approx(r2);
     if (CUTOFF) {
-        bool in = r2 < c.rc2;
-        if (KEEPTEST) in = in && keep;
+        const bool in = KEEPTEST ? (keep & (r2 < c.rc2)) : (r2 < c.rc2);   // one FSETP(.AND)
         ir2 = in ? ir2 : 0.0f;
     } else if (KEEPTEST) {
         ir2 = keep ? ir2 : 0.0f;
@@ -40,6 +39,72 @@ __device__ __forceinline__ void pair_accum(float xi, float yi, float xj, float y
     fx = fmaf(f, dx, fx);
     fy = fmaf(f, dy, fy);
     if (PE) pe = fmaf(ir6, fmaf(ir6, c.d12, -c.d6), pe);
+}
+
+// Two ordered pairs at once, (i0 <- j) and (i1 <- j), on Blackwell's packed-FP32 pipe
+// (FADD2 / FMUL2 / FFMA2 on aligned register pairs): the same arithmetic as pair_accum, one
+// issue slot per two pairs for every FMA-pipe operation.  The minimum image stays scalar
+// (compare + sign-merge + predicated add on each half) so it remains bit-identical to the
+// reference's div+round; r2 is still the unfused dx*dx + dy*dy.
+//   nxj2 / nyj2 hold (-xj, -xj) / (-yj, -yj): xi + (-xj) == xi - xj exactly.
+struct PairConsts2 {
+    float2 c12, nc6, d12, nd6, one;
+};
+__device__ __forceinline__ PairConsts2 make_pair_consts2(const PairConsts& c) {
+    PairConsts2 p;
+    p.c12 = make_float2(c.c12, c.c12);
+    p.nc6 = make_float2(-c.c6, -c.c6);
+    p.d12 = make_float2(c.d12, c.d12);
+    p.nd6 = make_float2(-c.d6, -c.d6);
+    p.one = make_float2(c.one, c.one);
+    return p;
+}
+
+// 32-bit L2 load that the compiler may not merge with its neighbour into a 64-bit load: the
+// packed path wants (x_i0, x_i1) in one aligned register pair, not (x_i0, y_i0).
+__device__ __forceinline__ float ldcg_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+// Pack two floats into ONE 64-bit register that stays live (volatile: ptxas may not
+// rematerialise it with two MOVs per use, which it otherwise does for loop-invariant pairs).
+__device__ __forceinline__ float2 pack_pinned(float lo, float hi) {
+    unsigned long long r;
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return *reinterpret_cast<float2*>(&r);
+}
+
+template <bool CUTOFF, bool PE, bool KEEPTEST>
+__device__ __forceinline__ void pair2_accum(float2 xi2, float2 yi2, float2 nxj2, float2 nyj2,
+                                            bool keep0, bool keep1, const PairConsts& c,
+                                            const PairConsts2& c2, float2& fx2, float2& fy2,
+                                            float2& pe2) {
+    float2 dx = __fadd2_rn(xi2, nxj2);
+    float2 dy = __fadd2_rn(yi2, nyj2);
+    dx.x = min_image(dx.x, c.box, c.timg);
+    dx.y = min_image(dx.y, c.box, c.timg);
+    dy.x = min_image(dy.x, c.box, c.timg);
+    dy.y = min_image(dy.y, c.box, c.timg);
+    // unfused dx*dx + dy*dy: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, so the add is
+    // written as fma(t, 1, u) with a run-time 1.0f (exact product, one rounding of the sum).
+    const float2 r2 = __ffma2_rn(__fmul2_rn(dx, dx), c2.one, __fmul2_rn(dy, dy));
+    float2 ir2 = make_float2(rcp_approx(r2.x), rcp_approx(r2.y));
+    if (CUTOFF) {
+        const bool in0 = KEEPTEST ? (keep0 & (r2.x < c.rc2)) : (r2.x < c.rc2);
+        const bool in1 = KEEPTEST ? (keep1 & (r2.y < c.rc2)) : (r2.y < c.rc2);
+        ir2.x = in0 ? ir2.x : 0.0f;
+        ir2.y = in1 ? ir2.y : 0.0f;
+    } else if (KEEPTEST) {
+        ir2.x = keep0 ? ir2.x : 0.0f;
+        ir2.y = keep1 ? ir2.y : 0.0f;
+    }
+    const float2 ir6 = __fmul2_rn(__fmul2_rn(ir2, ir2), ir2);
+    const float2 f = __fmul2_rn(__ffma2_rn(ir6, c2.c12, c2.nc6), __fmul2_rn(ir6, ir2));
+    fx2 = __ffma2_rn(f, dx, fx2);
+    fy2 = __ffma2_rn(f, dy, fy2);
+    if (PE) pe2 = __ffma2_rn(ir6, __ffma2_rn(ir6, c2.d12, c2.nd6), pe2);
 }
 
 // jnp.mod(x, box) of MD:72 (result has the divisor's sign; can return exactly `box` for tiny
@@ -100,17 +165,15 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 // A spin that lasts longer than ~2^32 clocks (about 2 s) raises *err and falls through, so a
 // lost rank can never hang the GPU.
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target, int* err) {
-    __syncthreads();
+    __syncthreads();                       // every thread's writes are ordered before thread 0's release
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         long long t0 = clock64();
         while (ld_acquire_gpu(counter) < target) {
             if (clock64() - t0 > (1ll << 32)) { atomicExch(err, 1); break; }
         }
-        __threadfence();
     }
-    __syncthreads();
+    __syncthreads();                       // ... and the acquire is ordered before every thread's reads
 }
 
 }  // namespace ljmd

@@ -37,6 +37,7 @@ void set_error(const char* fmt, ...);
 struct PairConsts {
     float box, timg, rc2;
     float c12, c6, d12, d6;
+    float one;      // 1.0f passed at run time (blocks an unwanted FMA contraction, see pair2_accum)
     int   cutoff;   // 0 = none (the reference), 1 = plain truncation at rc
 };
 
@@ -84,6 +85,7 @@ void ap_destroy(ljmd_handle* h);
 // nsteps == 0: evaluate F (optional) and PE (optional) of R_in only.
 int  ap_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_out, float2* V_out,
             float2* F_out, float* pe_out, const RunCtl& rc);
+int  ap_check_error(ljmd_handle* h);
 int  ap_gr_hist(ljmd_handle* h, const float2* R_hist, long long S, int nbins, const float* edges,
                 long long* counts);
 

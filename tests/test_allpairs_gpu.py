@@ -55,9 +55,16 @@ def test_net_force_zero_and_lattice(oracle):
     sim = _sim(N, rc=2.5)
     F = sim.force_fn(R).numpy()
     assert np.abs(F.sum(axis=0)).max() <= 1e-3 * np.abs(F).max()
+    # perfect lattice: a*sqrt(5) == rc == 2.5 exactly at rho = 0.8, so use the reference's
+    # no-cutoff form here (with rc the (1,2) neighbours sit on the truncation edge)
     Rl, _, _ = lattice_jitter(N, seed=0, jitter=0.0)
-    Fl = sim.force_fn(Rl).numpy()
+    sim0 = _sim(N, rc=None)
+    Fl = sim0.force_fn(Rl).numpy()
     assert np.abs(Fl).max() < 5e-4
+    # ... and with the cutoff the pair set must still be the oracle's, bit for bit in r2
+    Fl_rc = sim.force_fn(Rl).numpy()
+    Fc, _ = oracle.c_forces(Rl, box, rc=2.5)
+    assert np.abs(Fl_rc - Fc).max() <= 1e-5 * max(np.abs(Fc).max(), 1.0)
 
 
 def test_two_particles_across_seam():
