@@ -201,7 +201,8 @@ int ljmd_last_run_ms(ljmd_t* h, float* ms) {
     LJ_CUDA(cudaSetDevice(h->p.device));
     LJ_CUDA(cudaEventSynchronize(h->ev1));
     LJ_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
-    return ap_check_error(h);
+    int e = ap_check_error(h);
+    return e ? e : cells_check_error(h);
 }
 
 int ljmd_launch_count(ljmd_t* h, int64_t* launches) {

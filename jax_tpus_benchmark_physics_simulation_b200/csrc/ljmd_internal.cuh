@@ -98,6 +98,7 @@ int  cells_geometry(ljmd_handle* h, int* ncell, float* cell, float* inv_cell);
 int  cells_assign(ljmd_handle* h, const float2* R, int* cell_id, int* cell_count);
 int  cells_neighbor_count(ljmd_handle* h, const float2* R, float radius, int* nbr_count);
 long long cells_last_rebuilds(ljmd_handle* h);
+int  cells_check_error(ljmd_handle* h);
 
 // probe.cu
 int  fp32_peak_probe(int device, int packed, float* tflops);
