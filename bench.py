@@ -133,7 +133,6 @@ def run_reference(args, wl_name, wl):
     """--impl reference: the CPU restatement timed on this box's host cores (rank 0 only)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    import torch
     N, rc, dt = wl["N"], wl["rc"], wl["dt"]
     if wl["path"] == "cells":
         # no all-pairs CPU baseline exists at N >= 4M (1.8e13 pairs / evaluation): time the C
@@ -153,17 +152,24 @@ def run_reference(args, wl_name, wl):
         sample = "1 cell-grid force evaluation (C restatement, OpenMP) per step"
         md_per_step = 1
     else:
+        import torch
+        from oracle import lj_oracle as O
+        from jax_tpus_benchmark_physics_simulation_b200 import lattice_jitter
         md_per_step = 1
-        # warm-up steps are real steps too; keep the whole run within a few minutes
-        per, cores = cpu_reference_step_time(N, rc, dt, 1)
-        nwarm = max(0, args.warmup - 1)
-        for _ in range(nwarm):
-            cpu_reference_step_time(N, rc, dt, 1) if per < 2.0 else None
+        R, V, box = lattice_jitter(N, seed=0)
+        state = (torch.from_numpy(R), torch.from_numpy(V))
+        if N <= 8192:
+            ff = lambda r: O.force_autodiff(r, float(box), rc=rc)
+        else:   # N x N does not fit in memory: row-chunked restatement of the same formulas
+            ff = lambda r: O.force_analytic(r, float(box), rc=rc)[0]
         times = []
-        for _ in range(args.steps):
-            p, _ = cpu_reference_step_time(N, rc, dt, md_per_step)
-            times.append(p * md_per_step)
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            state = O.verlet_step(state, float(box), dt, ff)       # MD:66-75, 2 force evaluations
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t0)
         t = sum(times)
+        cores = torch.get_num_threads()
         sample = (f"{md_per_step} verlet_step (2 dense autodiff force evaluations, torch CPU fp32) "
                   "per bench step; restatement, JAX unavailable")
     value = N * md_per_step * args.steps / t
