@@ -45,6 +45,12 @@ constexpr float SENT_I   = -1.0e18f;
 struct ApArgs {
     PairConsts pc;
     int   N, G, NJu, nI, maxseg, ppc;   // ppc = particles owned per CTA in phase [d]
+    int   i_lo, Nloc;                   // this rank owns particles [i_lo, i_lo + Nloc) (atom decomposition)
+    int   rank, P;                      // P > 1: positions are pushed to every peer over NVLink
+    unsigned xepoch0;                   // cross-GPU barrier epochs already consumed by earlier launches
+    float2*   peerR0[LJMD_MAX_RANKS];   // every rank's ping-pong position buffers (peer-mapped)
+    float2*   peerR1[LJMD_MAX_RANKS];
+    unsigned* peer_flags[LJMD_MAX_RANKS];   // every rank's arrival words [P]; [rank] is the local one
     float dt;
     const long long* cta_start;   // [G+1] flat (i-block * NJu + j-unit) range owned by each CTA
     const int*       cta_ib0;     // [G]   first i-block a CTA touches
@@ -83,15 +89,15 @@ __device__ __forceinline__ void ap_segment(const ApArgs& a, const float2* __rest
     int   ii[IPT];
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
-        ii[k] = ib * BI + k * AP_THREADS + tid;
-        if (ii[k] < a.N) {
+        ii[k] = a.i_lo + ib * BI + k * AP_THREADS + tid;
+        if (ii[k] < a.i_lo + a.Nloc) {
             const float* rp = reinterpret_cast<const float*>(Rcur + ii[k]);
             xi[k] = ldcg_f32(rp); yi[k] = ldcg_f32(rp + 1);
         } else { xi[k] = SENT_I; yi[k] = SENT_I; }
         fx[k] = 0.0f; fy[k] = 0.0f;
     }
     const int j0 = ju0 * J_UNIT, jend = (ju0 + julen) * J_UNIT;
-    const int i_lo = ib * BI, i_hi = i_lo + BI;
+    const int i_lo = a.i_lo + ib * BI, i_hi = i_lo + BI;
 
     for (int jt = j0; jt < jend; jt += TILE_J) {
         const int cnt = min(TILE_J, jend - jt);           // multiple of J_UNIT
@@ -232,10 +238,11 @@ ap_persistent_kernel(const ApArgs a) {
         // lane 0 of the group integrates it.  Fixed order => bit-reproducible, no atomics.
         float ke_thread = 0.0f;
         const int grp = tid / RED_LANES, gl = tid % RED_LANES;
-        const int g_end = min(a.N, (c + 1) * a.ppc);
+        const int g_end = min(a.Nloc, (c + 1) * a.ppc);                          // slab-local indices
         for (int gb = c * a.ppc; gb < g_end; gb += AP_THREADS / RED_LANES) {   // block-uniform trip count
-            const int g = gb + grp;
-            const bool live = g < g_end;
+            const int gloc = gb + grp;
+            const int g = a.i_lo + gloc;                                       // global particle index
+            const bool live = gloc < g_end;
             float Fx = 0.0f, Fy = 0.0f;
             float2 r = make_float2(0.0f, 0.0f), v = make_float2(0.0f, 0.0f);
             if (live && gl == 0) {                          // issued early: overlaps the partial loads
@@ -243,7 +250,7 @@ ap_persistent_kernel(const ApArgs a) {
                 if (rc.nsteps > 0) v = a.Vh[g];
             }
             if (live) {
-                const int ib = g / BI, il = g - ib * BI;
+                const int ib = gloc / BI, il = gloc - ib * BI;
                 const int2 cc = a.iblk_ctas[ib];
 #pragma unroll 4
                 for (int c2 = cc.x + gl; c2 <= cc.y; c2 += RED_LANES) {
@@ -273,10 +280,17 @@ ap_persistent_kernel(const ApArgs a) {
             } else {
                 v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt);                // MD:70
                 a.Vh[g] = v;
-                __stcg(&Rnext[g], make_float2(drift(r.x, v.x, a.dt, a.pc.box),      // MD:71-72
-                                              drift(r.y, v.y, a.dt, a.pc.box)));
+                const float2 rn = make_float2(drift(r.x, v.x, a.dt, a.pc.box),      // MD:71-72
+                                              drift(r.y, v.y, a.dt, a.pc.box));
+                __stcg(&Rnext[g], rn);
+                if (a.P > 1) {                               // position "all-gather": direct NVLink stores
+                    const int nb = (int)((s + 1) & 1);
+                    for (int q = 0; q < a.P; ++q)
+                        if (q != a.rank) (nb ? a.peerR1[q] : a.peerR0[q])[g] = rn;
+                }
             }
         }
+        if (a.P > 1) __threadfence_system();                 // peer stores visible before the arrival
         if (want_e || thermo) {
             float t = block_sum<AP_THREADS>(ke_thread, sred);
             if (tid == 0) __stcg(&a.ke_part[par * a.G + c], t);
@@ -288,12 +302,13 @@ ap_persistent_kernel(const ApArgs a) {
                 double ke2 = warp_sum_array(a.ke_part + par * a.G, a.G);
                 if (tid == 0) {
                     float ke = (float)(0.5 * ke2);
-                    s_lambda = sqrtf(rc.thermo_kT / (ke / (float)a.N));
+                    s_lambda = sqrtf(rc.thermo_kT / (ke / (float)a.N));   // (single-GPU only)
                 }
             }
             __syncthreads();
             const float lam = s_lambda;
-            for (int g = c * a.ppc + tid; g < g_end; g += AP_THREADS) {
+            for (int gloc = c * a.ppc + tid; gloc < g_end; gloc += AP_THREADS) {
+                const int g = a.i_lo + gloc;
                 const float2 r = __ldcg(&Rcur[g]);
                 const float2 F = a.Ftmp[g];
                 float2 v = a.Vh[g];
@@ -312,6 +327,28 @@ ap_persistent_kernel(const ApArgs a) {
         }
         if (prof) { long long t = clock64(); pt[2] += t - pt[4]; pt[4] = t; }
         grid_barrier(a.bar, (++epoch) * (unsigned)a.G, a.err);
+        if (a.P > 1 && !final) {
+            // every rank has pushed its slab into our next-position buffer once all P arrival words
+            // carry this epoch: one NVLink round trip per step, no NCCL on the step path
+            const unsigned xe = a.xepoch0 + (unsigned)(s - a.s_begin) + 1u;
+            if (c == 0 && tid < a.P && tid != a.rank) {
+                __threadfence_system();
+                volatile unsigned* f = a.peer_flags[tid] + a.rank;
+                *f = xe;
+            }
+            if (tid == 0) {
+                const volatile unsigned* mine = a.peer_flags[a.rank];
+                long long t0 = clock64();
+                for (int q = 0; q < a.P; ++q) {
+                    if (q == a.rank) continue;
+                    while ((int)(mine[q] - xe) < 0) {
+                        if (clock64() - t0 > (1ll << 33)) { atomicExch(a.err, 2); break; }
+                    }
+                }
+                __threadfence_system();
+            }
+            __syncthreads();
+        }
         if (prof) { long long t = clock64(); pt[3] += t - pt[4]; pt[4] = t; }
 
         // ---- energies of the post-step state (one warp, fixed order, double combine) ----------
@@ -403,6 +440,13 @@ struct AllPairs {
     int2*      d_iblk = nullptr;
     float2 *Rbuf0 = nullptr, *Rbuf1 = nullptr, *Vh = nullptr, *Ftmp = nullptr, *part = nullptr;
     float *pe_part = nullptr, *ke_part = nullptr;
+    int i_lo = 0, Nloc = 0;
+    void* shared = nullptr;             // one allocation (IPC-shareable): Rbuf0 | Rbuf1 | arrival words
+    unsigned* xflags = nullptr;
+    unsigned  xepoch = 0;
+    float2*   peerR0[LJMD_MAX_RANKS] = {};
+    float2*   peerR1[LJMD_MAX_RANKS] = {};
+    unsigned* peer_flags[LJMD_MAX_RANKS] = {};
     unsigned* bar = nullptr;
     int* err = nullptr;
     long long* prof = nullptr;
@@ -416,7 +460,11 @@ int ap_create(ljmd_handle* h) {
     ap->ipt = (N >= 2048) ? 2 : 1;
     if (const char* e = getenv("LJMD_AP_IPT")) ap->ipt = (atoi(e) == 2) ? 2 : 1;
     const int BI = AP_THREADS * ap->ipt;
-    ap->nI  = (int)((N + BI - 1) / BI);
+    const int P = std::max(1, h->nranks);
+    if (N % P != 0) { set_error("all-pairs atom decomposition needs N divisible by the rank count"); return LJMD_E_INVALID; }
+    ap->Nloc = (int)(N / P);
+    ap->i_lo = h->rank * ap->Nloc;
+    ap->nI  = (ap->Nloc + BI - 1) / BI;             // i-blocks of THIS rank's slab
     ap->NJu = (int)((N + J_UNIT - 1) / J_UNIT);
     ap->kernel = pick_kernel(ap->ipt, h->pc.cutoff != 0);
 
@@ -437,7 +485,7 @@ int ap_create(ljmd_handle* h) {
     const long long W_PLAIN = 100, W_DIAG = (ap->ipt == 2) ? 116 : 110;
     const int du = BI / J_UNIT;                       // diagonal units per row
     auto row_cost = [&](int b, long long u) {         // cost of units [0, u) of row b
-        const long long d0 = std::min<long long>((long long)b * du, ap->NJu);
+        const long long d0 = std::min<long long>((long long)ap->i_lo / J_UNIT + (long long)b * du, ap->NJu);
         const long long d1 = std::min<long long>(d0 + du, ap->NJu);
         const long long nd = std::max<long long>(0, std::min(u, d1) - d0);
         return u * W_PLAIN + nd * (W_DIAG - W_PLAIN);
@@ -487,8 +535,28 @@ int ap_create(ljmd_handle* h) {
     LJ_CUDA(cudaMemcpy(ap->d_cta_start, start.data(), sizeof(long long) * (ap->G + 1), cudaMemcpyHostToDevice));
     LJ_CUDA(cudaMemcpy(ap->d_cta_ib0, ib0.data(), sizeof(int) * ap->G, cudaMemcpyHostToDevice));
     LJ_CUDA(cudaMemcpy(ap->d_iblk, iblk.data(), sizeof(int2) * ap->nI, cudaMemcpyHostToDevice));
-    LJ_CUDA(cudaMalloc(&ap->Rbuf0, sizeof(float2) * N));
-    LJ_CUDA(cudaMalloc(&ap->Rbuf1, sizeof(float2) * N));
+    {   // one >= 2 MiB allocation so that its IPC handle maps exactly this region on the peers
+        const size_t rb = (sizeof(float2) * (size_t)N + 255) / 256 * 256;
+        size_t bytes = 2 * rb + 256;
+        bytes = std::max<size_t>((bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20), 4u << 20);
+        LJ_CUDA(cudaMalloc(&ap->shared, bytes));
+        LJ_CUDA(cudaMemset(ap->shared, 0, bytes));
+        ap->Rbuf0 = reinterpret_cast<float2*>(ap->shared);
+        ap->Rbuf1 = reinterpret_cast<float2*>(reinterpret_cast<char*>(ap->shared) + rb);
+        ap->xflags = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ap->shared) + 2 * rb);
+        ap->peerR0[h->rank] = ap->Rbuf0; ap->peerR1[h->rank] = ap->Rbuf1; ap->peer_flags[h->rank] = ap->xflags;
+        if (P > 1) {
+            void* peers[LJMD_MAX_RANKS];
+            int r = dist_share(h, ap->shared, peers);
+            if (r) return r;
+            for (int q = 0; q < P; ++q) {
+                char* base = reinterpret_cast<char*>(peers[q]);
+                ap->peerR0[q] = reinterpret_cast<float2*>(base);
+                ap->peerR1[q] = reinterpret_cast<float2*>(base + rb);
+                ap->peer_flags[q] = reinterpret_cast<unsigned*>(base + 2 * rb);
+            }
+        }
+    }
     LJ_CUDA(cudaMalloc(&ap->Vh, sizeof(float2) * N));
     LJ_CUDA(cudaMalloc(&ap->Ftmp, sizeof(float2) * N));
     LJ_CUDA(cudaMalloc(&ap->part, sizeof(float2) * (size_t)ap->G * ap->maxseg * BI));
@@ -505,7 +573,7 @@ void ap_destroy(ljmd_handle* h) {
     AllPairs* ap = h->ap;
     if (!ap) return;
     cudaFree(ap->d_cta_start); cudaFree(ap->d_cta_ib0); cudaFree(ap->d_iblk);
-    cudaFree(ap->Rbuf0); cudaFree(ap->Rbuf1); cudaFree(ap->Vh); cudaFree(ap->Ftmp);
+    cudaFree(ap->shared); cudaFree(ap->Vh); cudaFree(ap->Ftmp);
     cudaFree(ap->part); cudaFree(ap->pe_part); cudaFree(ap->ke_part);
     cudaFree(ap->bar); cudaFree(ap->err);
     delete ap;
@@ -524,7 +592,10 @@ int ap_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_out
     }
     ApArgs a{};
     a.pc = h->pc;
-    a.ppc = (int)((N + ap->G - 1) / ap->G);
+    a.ppc = (ap->Nloc + ap->G - 1) / ap->G;
+    a.i_lo = ap->i_lo; a.Nloc = ap->Nloc; a.rank = h->rank; a.P = std::max(1, h->nranks);
+    for (int q = 0; q < LJMD_MAX_RANKS; ++q) { a.peerR0[q] = ap->peerR0[q]; a.peerR1[q] = ap->peerR1[q]; a.peer_flags[q] = ap->peer_flags[q]; }
+    if (a.P > 1 && rc.thermo_every > 0) { set_error("the rescale thermostat is single-GPU only"); return LJMD_E_UNSUPPORTED; }
     a.N = (int)N; a.G = ap->G; a.NJu = ap->NJu; a.nI = ap->nI; a.maxseg = ap->maxseg;
     a.dt = h->p.dt;
     a.cta_start = ap->d_cta_start; a.cta_ib0 = ap->d_cta_ib0; a.iblk_ctas = ap->d_iblk;
@@ -545,11 +616,28 @@ int ap_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_out
     while (s < s_last) {
         const long long e = std::min(s_last, s + chunk);
         a.s_begin = s; a.s_end = e;
+        a.xepoch0 = ap->xepoch;
         LJ_CUDA(cudaMemsetAsync(ap->bar, 0, sizeof(unsigned), st));
         void* args[] = {(void*)&a};
         LJ_CUDA(cudaLaunchCooperativeKernel((void*)ap->kernel, dim3(ap->G), dim3(AP_THREADS), args, 0, st));
         h->launches++;
+        ap->xepoch += (unsigned)(e - s);             // one cross-GPU epoch per step of the launch
         s = e;
+    }
+    if (a.P > 1) {
+        // replicated out: slabs of the final state -> every rank (NCCL, once per call, not per step)
+        const size_t slab = sizeof(float2) * (size_t)ap->Nloc;
+        int r = 0;
+        if (R_out && (r = dist_allgather(h, R_out, slab))) return r;
+        if (V_out && (r = dist_allgather(h, V_out, slab))) return r;
+        if (F_out && (r = dist_allgather(h, F_out, slab))) return r;
+        for (long long k = 0; rc.traj && k < rc.S; ++k)
+            if ((r = dist_allgather(h, rc.traj + (size_t)k * N, slab))) return r;
+        if (pe_out && (r = dist_allreduce_f32(h, pe_out, 1))) return r;
+        if (rc.ke_pe && rc.energy_every > 0) {       // "energies use one NCCL all-reduce"
+            const long long ne = (rc.nsteps + rc.energy_every - 1) / rc.energy_every;
+            if ((r = dist_allreduce_f32(h, rc.ke_pe, (size_t)(2 * ne)))) return r;
+        }
     }
     if (h->timed) LJ_CUDA(cudaEventRecord(h->ev1, st));
     if (ap->prof) {   // debug: mean / max clocks per phase per step of the last launch

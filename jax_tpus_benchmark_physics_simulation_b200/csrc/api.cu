@@ -37,9 +37,11 @@ PairConsts make_pair_consts(float box, float sigma, float eps, float rc) {
     return c;
 }
 
-static int create_common(ljmd_t** out, const ljmd_params* p, int rank, int nranks) {
+int create_common(ljmd_t** out, const ljmd_params* p, int rank, int nranks, const void* nccl_uid) {
     if (!out || !p) { set_error("null argument"); return LJMD_E_INVALID; }
     *out = nullptr;
+    if (nranks < 1 || nranks > LJMD_MAX_RANKS || rank < 0 || rank >= nranks) { set_error("bad rank %d / nranks %d (max %d)", rank, nranks, LJMD_MAX_RANKS); return LJMD_E_INVALID; }
+    if (nranks > 1 && !nccl_uid) { set_error("missing NCCL unique id"); return LJMD_E_INVALID; }
     if (p->N < 2 || p->N > (1ll << 30)) { set_error("N out of range: %lld", (long long)p->N); return LJMD_E_INVALID; }
     if (!(p->box > 0.0f) || !std::isfinite(p->box)) { set_error("box must be positive and finite"); return LJMD_E_INVALID; }
     if (!(p->sigma > 0.0f) || !(p->epsilon > 0.0f)) { set_error("sigma and epsilon must be positive"); return LJMD_E_INVALID; }
@@ -79,7 +81,15 @@ static int create_common(ljmd_t** out, const ljmd_params* p, int rank, int nrank
         delete h;
         return rcode;
     }
-    // the all-pairs engine is always present: it also serves ljmd_gr_hist and small-N fallbacks
+    if (nranks > 1) {
+        if (path != LJMD_PATH_ALLPAIRS) {
+            set_error("multi-GPU: only the all-pairs path is sharded in this build (cell-list slabs: see DESIGN.md)");
+            ljmd_destroy(h);
+            return LJMD_E_UNSUPPORTED;
+        }
+        rcode = dist_init(h, nccl_uid);
+        if (rcode) { ljmd_destroy(h); return rcode; }
+    }
     rcode = (path == LJMD_PATH_ALLPAIRS) ? ap_create(h) : cells_create(h);
     if (rcode) { ljmd_destroy(h); return rcode; }
     *out = h;
@@ -95,7 +105,7 @@ extern "C" {
 int ljmd_abi_version(void) { return LJMD_ABI_VERSION; }
 const char* ljmd_last_error(void) { return g_err; }
 
-int ljmd_create(ljmd_t** out, const ljmd_params* p) { return create_common(out, p, 0, 1); }
+int ljmd_create(ljmd_t** out, const ljmd_params* p) { return create_common(out, p, 0, 1, nullptr); }
 
 void ljmd_destroy(ljmd_t* h) {
     if (!h) return;
@@ -103,6 +113,7 @@ void ljmd_destroy(ljmd_t* h) {
     cudaStreamSynchronize(h->stream);
     ap_destroy(h);
     cells_destroy(h);
+    dist_destroy(h);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;

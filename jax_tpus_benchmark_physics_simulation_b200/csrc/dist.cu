@@ -1,10 +1,157 @@
-// dist.cu — multi-GPU entry points (placeholder until the single-GPU paths are green).
+// dist.cu — multi-GPU plumbing (new; the reference script is single-device).
+//
+// One process per GPU.  NCCL (over NVLink 5 / NVSwitch) is used for what happens ONCE per call:
+// bootstrap (exchange of CUDA-IPC handles), replication of the final state, and the single
+// all-reduce of the energy trace.  The per-step position exchange is NOT an NCCL call: the
+// all-pairs kernel's integrate epilogue stores each new position straight into every peer's
+// next-position buffer through the IPC-mapped peer pointers set up here, and a per-step arrival
+// word per rank replaces the collective's synchronisation (allpairs.cu).
+//
+// libnccl is dlopen()ed so that single-GPU users need no NCCL at all; inside a torch process the
+// soname resolves to the copy torch already loaded (one NCCL per process).
 #include "ljmd_internal.cuh"
+
+#include <dlfcn.h>
+#include <cstring>
+
+namespace ljmd {
+
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclFloat32 = 7, ncclInt8 = 0, ncclSum = 0 };
+
+struct Nccl {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+Nccl g_nccl;
+
+int load_nccl() {
+    if (g_nccl.lib) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) { set_error("cannot dlopen libnccl.so.2: %s", dlerror()); return LJMD_E_NCCL; }
+#define LJ_SYM(field, name)                                                        \
+    *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, name);                            \
+    if (!g_nccl.field) { set_error("libnccl lacks %s", name); return LJMD_E_NCCL; }
+    LJ_SYM(GetUniqueId, "ncclGetUniqueId")
+    LJ_SYM(CommInitRank, "ncclCommInitRank")
+    LJ_SYM(CommDestroy, "ncclCommDestroy")
+    LJ_SYM(AllGather, "ncclAllGather")
+    LJ_SYM(AllReduce, "ncclAllReduce")
+    LJ_SYM(GetErrorString, "ncclGetErrorString")
+#undef LJ_SYM
+    return 0;
+}
+
+#define LJ_NCCL(expr)                                                              \
+    do {                                                                           \
+        int _r = (expr);                                                           \
+        if (_r != 0) {                                                             \
+            set_error("%s failed: %s", #expr, g_nccl.GetErrorString(_r));          \
+            return LJMD_E_NCCL;                                                    \
+        }                                                                          \
+    } while (0)
+
+}  // namespace
+
+struct Dist {
+    ncclComm_t comm = nullptr;
+    void* peer_mapped[LJMD_MAX_RANKS] = {};
+    int n_mapped = 0;
+};
+
+int dist_init(ljmd_handle* h, const void* nccl_unique_id) {
+    int r = load_nccl();
+    if (r) return r;
+    Dist* d = new Dist();
+    h->dist = d;
+    ncclUniqueId id;
+    memcpy(&id, nccl_unique_id, sizeof(id));
+    LJ_NCCL(g_nccl.CommInitRank(&d->comm, h->nranks, id, h->rank));
+    return 0;
+}
+
+void dist_destroy(ljmd_handle* h) {
+    Dist* d = h->dist;
+    if (!d) return;
+    for (int q = 0; q < LJMD_MAX_RANKS; ++q)
+        if (d->peer_mapped[q]) cudaIpcCloseMemHandle(d->peer_mapped[q]);
+    if (d->comm) g_nccl.CommDestroy(d->comm);
+    delete d;
+    h->dist = nullptr;
+}
+
+// Exchange the CUDA-IPC handle of `local_base` (the base of one cudaMalloc allocation) with all
+// ranks through NCCL and map every peer's allocation into this process.
+int dist_share(ljmd_handle* h, void* local_base, void** peer_bases) {
+    Dist* d = h->dist;
+    if (!d) { set_error("dist_share without a communicator"); return LJMD_E_STATE; }
+    cudaIpcMemHandle_t mine;
+    LJ_CUDA(cudaIpcGetMemHandle(&mine, local_base));
+    char* dev = nullptr;
+    const size_t hs = sizeof(cudaIpcMemHandle_t);
+    LJ_CUDA(cudaMalloc(&dev, hs * h->nranks));
+    LJ_CUDA(cudaMemcpy(dev + hs * h->rank, &mine, hs, cudaMemcpyHostToDevice));
+    LJ_NCCL(g_nccl.AllGather(dev + hs * h->rank, dev, hs, ncclInt8, d->comm, h->stream));
+    LJ_CUDA(cudaStreamSynchronize(h->stream));
+    cudaIpcMemHandle_t all[LJMD_MAX_RANKS];
+    LJ_CUDA(cudaMemcpy(all, dev, hs * h->nranks, cudaMemcpyDeviceToHost));
+    LJ_CUDA(cudaFree(dev));
+    for (int q = 0; q < h->nranks; ++q) {
+        if (q == h->rank) { peer_bases[q] = local_base; continue; }
+        void* pq = nullptr;
+        LJ_CUDA(cudaIpcOpenMemHandle(&pq, all[q], cudaIpcMemLazyEnablePeerAccess));
+        peer_bases[q] = pq;
+        d->peer_mapped[q] = pq;
+    }
+    return 0;
+}
+
+int dist_allgather(ljmd_handle* h, void* buf, size_t bytes_per_rank) {
+    Dist* d = h->dist;
+    char* b = reinterpret_cast<char*>(buf);
+    LJ_NCCL(g_nccl.AllGather(b + bytes_per_rank * h->rank, b, bytes_per_rank, ncclInt8, d->comm, h->stream));
+    return 0;
+}
+
+int dist_allreduce_f32(ljmd_handle* h, float* buf, size_t n) {
+    Dist* d = h->dist;
+    LJ_NCCL(g_nccl.AllReduce(buf, buf, n, ncclFloat32, ncclSum, d->comm, h->stream));
+    return 0;
+}
+
+}  // namespace ljmd
+
+using namespace ljmd;
+
 extern "C" {
-int ljmd_get_unique_id(void*) { ljmd::set_error("multi-GPU not built yet"); return LJMD_E_UNSUPPORTED; }
-int ljmd_create_dist(ljmd_t** out, const ljmd_params*, const void*, int32_t, int32_t) {
-    if (out) *out = nullptr;
-    ljmd::set_error("multi-GPU not built yet");
-    return LJMD_E_UNSUPPORTED;
+
+int ljmd_get_unique_id(void* id128) {
+    if (!id128) { set_error("null argument"); return LJMD_E_INVALID; }
+    int r = load_nccl();
+    if (r) return r;
+    ncclUniqueId id;
+    LJ_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return 0;
 }
+
+int ljmd_create_dist(ljmd_t** out, const ljmd_params* p, const void* nccl_unique_id, int32_t rank,
+                     int32_t nranks) {
+    if (nranks == 1) return create_common(out, p, 0, 1, nullptr);
+    return create_common(out, p, rank, nranks, nccl_unique_id);
 }
+
+}  // extern "C"

@@ -10,6 +10,8 @@
 
 #include "../../include/ljmd.h"
 
+#define LJMD_MAX_RANKS 8
+
 namespace ljmd {
 
 void set_error(const char* fmt, ...);
@@ -99,6 +101,16 @@ int  cells_assign(ljmd_handle* h, const float2* R, int* cell_id, int* cell_count
 int  cells_neighbor_count(ljmd_handle* h, const float2* R, float radius, int* nbr_count);
 long long cells_last_rebuilds(ljmd_handle* h);
 int  cells_check_error(ljmd_handle* h);
+
+// api.cu
+int  create_common(ljmd_t** out, const ljmd_params* p, int rank, int nranks, const void* nccl_uid);
+
+// dist.cu (NCCL over NVLink for bootstrap / final replication; IPC peer mapping)
+int  dist_init(ljmd_handle* h, const void* nccl_unique_id);
+void dist_destroy(ljmd_handle* h);
+int  dist_share(ljmd_handle* h, void* local_base, void** peer_bases /*[nranks]*/);
+int  dist_allgather(ljmd_handle* h, void* buf, size_t bytes_per_rank);   // in place, slab `rank`
+int  dist_allreduce_f32(ljmd_handle* h, float* buf, size_t n);
 
 // probe.cu
 int  fp32_peak_probe(int device, int packed, float* tflops);

@@ -312,6 +312,39 @@ class LJSimulation:
         return v.value
 
 
+def slab_range(N: int, rank: int, nranks: int) -> Tuple[int, int]:
+    """Atom decomposition of the all-pairs path: rank p owns i-rows [p*N/P, (p+1)*N/P)
+    (SURVEY.md §8e).  N must be divisible by the rank count."""
+    if nranks < 1 or not (0 <= rank < nranks):
+        raise ValueError(f"bad rank {rank} / nranks {nranks}")
+    if N % nranks != 0:
+        raise ValueError(f"N={N} is not divisible by nranks={nranks}")
+    n = N // nranks
+    return rank * n, (rank + 1) * n
+
+
+def broadcast_unique_id(rank: int, get_uid=None) -> bytes:
+    """Rank 0 creates the 128-byte NCCL unique id (ljmd_get_unique_id) and broadcasts it over the
+    already-initialised torch.distributed group (any backend: gloo on CPU, nccl on GPUs)."""
+    import torch.distributed as dist
+    if get_uid is None:
+        def get_uid():
+            buf = ctypes.create_string_buffer(128)
+            _lib.check(_lib.load().ljmd_get_unique_id(buf), "ljmd_get_unique_id")
+            return buf.raw
+    box = [get_uid() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    uid = bytes(box[0])
+    if len(uid) != 128:
+        raise _lib.LjmdError(f"NCCL unique id must be 128 bytes, got {len(uid)}")
+    return uid
+
+
+def make_dist_arg(rank: int, nranks: int):
+    """(uid, rank, nranks) for ``LJSimulation(dist=...)``: one handle per rank / GPU."""
+    return broadcast_unique_id(rank), rank, nranks
+
+
 def fp32_peak_probe(device: int = 0, packed: bool = False) -> float:
     """Measured FP32 CUDA-core ceiling in TFLOP/s (FFMA or FFMA2 dependent chains)."""
     v = ctypes.c_float()
