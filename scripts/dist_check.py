@@ -18,9 +18,10 @@ one = LJSimulation(N, rc=2.5, dt=0.005, path="allpairs", device=lr)
 F, pe = sim.force_and_energy(R)
 F1, pe1 = one.force_and_energy(R)
 ferr = float(np.abs(F.numpy() - F1.numpy()).max() / np.abs(F1.numpy()).max())
-(Rs, Vs), traj = sim.run((R, V), steps, sample_every=10, energy_every=10)
+se = max(1, min(10, steps // 2))
+(Rs, Vs), traj = sim.run((R, V), steps, sample_every=se, energy_every=se)
 es = sim.last_energies.numpy()
-(Ro, Vo), traj1 = one.run((R, V), steps, sample_every=10, energy_every=10)
+(Ro, Vo), traj1 = one.run((R, V), steps, sample_every=se, energy_every=se)
 eo = one.last_energies.numpy()
 d = np.abs(Rs.numpy() - Ro.numpy()); d = np.minimum(d, float(box) - d)
 terr = np.abs(traj.numpy() - traj1.numpy()); terr = np.minimum(terr, float(box) - terr)

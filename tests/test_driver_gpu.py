@@ -1,0 +1,44 @@
+"""The reference's main() with the hot path swapped (driver.py) and the multi-GPU check."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_driver_default_flags_small(tmp_path):
+    """Same CLI as MD:196-213; runs equilibrate -> production -> g(r) with the three syncs."""
+    from jax_tpus_benchmark_physics_simulation_b200 import driver
+    out = str(tmp_path / "g_r_plot.png")
+    args = driver.build_parser().parse_args(
+        ["--N", "400", "--eq_steps", "300", "--prod_steps", "300", "--sample_every", "100",
+         "--output", out, "--energy_every", "100"])
+    assert args.rho == 0.8 and args.kT == 1.0 and args.dt == 1e-3 and args.seed == 42   # MD defaults
+    state_final, R_history, (r, g) = driver.main(args)
+    assert R_history.shape == (3, 400, 2)
+    assert np.isfinite(g).all() and g[:10].max() == 0.0 and 0.5 < g[-20:].mean() < 1.5
+    assert os.path.exists(out) or os.path.exists(out.rsplit(".", 1)[0] + ".npy")
+    pos = state_final[0].numpy()
+    assert np.isfinite(pos).all()
+
+
+def test_reference_defaults_match_parser():
+    from jax_tpus_benchmark_physics_simulation_b200 import driver
+    a = driver.build_parser().parse_args([])
+    assert (a.N, a.eq_steps, a.prod_steps, a.sample_every, a.output) == (400, 10000, 10000, 100, "g_r_plot.png")
+    assert a.rc is None          # the reference has no cutoff
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_allpairs_matches_single_gpu():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29541",
+           os.path.join(ROOT, "scripts", "dist_check.py"), "16384", "30"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("-> OK") == 2
