@@ -42,7 +42,7 @@ extern "C" {
 /* force-path selection */
 #define LJMD_PATH_AUTO      0   /* all-pairs for N <= 131072, else cell list      */
 #define LJMD_PATH_ALLPAIRS  1   /* dense N x N, the reference's formulation MD:50-62 */
-#define LJMD_PATH_CELLS     2   /* sorted cell list + 3x3 stencil (requires rc)   */
+#define LJMD_PATH_CELLS     2   /* sorted strip cells, 3 contiguous ranges / particle (requires rc) */
 
 typedef struct ljmd_handle ljmd_t;
 
@@ -105,10 +105,15 @@ int ljmd_gr_hist(ljmd_t* h, const float* R_hist, int64_t S, int32_t nbins,
                  const float* edges, int64_t* counts);
 
 /* ---- cell-list introspection (for the bit-exact CPU recount, north_star) -------- */
-/* geometry chosen at create: cells per side, cell edge (fp32), 1/cell edge (fp32)  */
-int ljmd_cell_geometry(ljmd_t* h, int32_t* ncell_side, float* cell_size, float* inv_cell);
+/* geometry chosen at create: the box is cut into `nrows` rows of height >= rc+skin and each row
+ * into `nbins_x` bins of width >= (rc+skin)/kbins; cell id = row * nbins_x + bin with
+ * row = min((int)(y * inv_row_height), nrows-1), bin = min((int)(x * inv_bin_width), nbins_x-1)
+ * (one fp32 multiply, truncation).  A particle's candidates are bins [bin-kbins, bin+kbins] of
+ * rows row-1, row, row+1 (periodic).                                                      */
+int ljmd_cell_geometry(ljmd_t* h, int32_t* nrows, int32_t* nbins_x, int32_t* kbins,
+                       float* inv_row_height, float* inv_bin_width);
 /* bins R, returns per-particle cell id (device int32[N]) and per-cell counts
- * (device int32[ncell^2]).  Either pointer may be NULL.                            */
+ * (device int32[nrows*nbins_x]).  Either pointer may be NULL.                            */
 int ljmd_cell_assign(ljmd_t* h, const float* R, int32_t* cell_id, int32_t* cell_count);
 /* per-particle number of neighbours with minimum-image r^2 < radius^2 (j != i), found
  * through the cell list.  nbr_count: device int32[N] in ORIGINAL particle order.     */

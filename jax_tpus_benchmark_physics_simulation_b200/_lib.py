@@ -68,7 +68,8 @@ def load() -> ctypes.CDLL:
     lib.ljmd_forces.argtypes = [vp, vp, vp, vp]
     lib.ljmd_run.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp, i64, vp, f32, i64]
     lib.ljmd_gr_hist.argtypes = [vp, vp, i64, i32, vp, vp]
-    lib.ljmd_cell_geometry.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(f32), ctypes.POINTER(f32)]
+    lib.ljmd_cell_geometry.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32),
+                                       ctypes.POINTER(f32), ctypes.POINTER(f32)]
     lib.ljmd_cell_assign.argtypes = [vp, vp, vp, vp]
     lib.ljmd_neighbor_count.argtypes = [vp, vp, f32, vp]
     lib.ljmd_last_rebuilds.argtypes = [vp, ctypes.POINTER(i64)]

@@ -179,10 +179,11 @@ int ljmd_gr_hist(ljmd_t* h, const float* R_hist, int64_t S, int32_t nbins, const
                       reinterpret_cast<long long*>(counts));
 }
 
-int ljmd_cell_geometry(ljmd_t* h, int32_t* ncell_side, float* cell_size, float* inv_cell) {
+int ljmd_cell_geometry(ljmd_t* h, int32_t* nrows, int32_t* nbins_x, int32_t* kbins,
+                       float* inv_row_height, float* inv_bin_width) {
     if (!h) { set_error("null handle"); return LJMD_E_INVALID; }
     if (h->path != LJMD_PATH_CELLS) { set_error("handle is not on the cell-list path"); return LJMD_E_STATE; }
-    return cells_geometry(h, ncell_side, cell_size, inv_cell);
+    return cells_geometry(h, nrows, nbins_x, kbins, inv_row_height, inv_bin_width);
 }
 
 int ljmd_cell_assign(ljmd_t* h, const float* R, int32_t* cell_id, int32_t* cell_count) {

@@ -1,27 +1,34 @@
-// cells.cu — sorted cell-list / compressed Verlet-list path for large N (BASELINE configs 4-5).
+// cells.cu — sorted strip-cell path for large N (BASELINE configs 4-5).
 //
 // Not in the reference (it only has the dense O(N^2) form, MD:51): the pair arithmetic is the
 // same as the all-pairs path (subtract, exact min-image, unfused r2, r2 < rc^2), so on identical
 // fp32 inputs it evaluates exactly the pair set of the all-pairs+cutoff oracle.
 //
-// Data layout in HBM (all in CELL-SORTED order, rebuilt only when the skin is exhausted):
-//   Rs[2]    float2  positions, ping-pong by step (the read buffer is never written in a step)
-//   Vh[2]    float2  velocities (buffers swap at a rebuild)
-//   orig[2]  int32   original particle index of each sorted slot
-//   Rbuild   float2  positions at the last rebuild (max-displacement test against skin/2)
-//   meta     uint32  neighbour count | edge flag << 8 (particle of a boundary cell)
-//   nbr2     uint32  compressed Verlet list, 2 neighbours per word, ELL layout
-//                    nbr2[(s / 2) * Npad + i]; each neighbour is the int16 index distance j - i
-//                    in sorted order (folded modulo N for the periodic top/bottom rows): sorted
-//                    row-major cell order keeps every neighbour within +-(one cell row + 64)
-//                    slots, so 2 bytes replace a 4-byte index and decode is one add
-//   cell_start int32 prefix-sum cell index over ncell^2 cells (cells in row-major order)
+// Geometry.  The box is cut into `nrows` horizontal rows of height >= rc + skin and every row into
+// `nbx` narrow bins of width >= (rc + skin) / K  (K = 4).  Cells (row, bin) are numbered row-major
+// and the particle state is kept SORTED by cell.  Everything within rc + skin of a particle of cell
+// (r, b) lies in bins [b-K, b+K] of rows r-1, r, r+1, i.e. in THREE CONTIGUOUS RANGES of the sorted
+// arrays: no neighbour list is stored, built or gathered; the per-step pass streams contiguous,
+// vectorised position loads (9 narrow bins per row = 42 candidates/particle at rho 0.8, against 57
+// for square 3x3 cells) and the rebuild is only a counting sort.
 //
-// One PERSISTENT cooperative kernel runs a whole ljmd_run(): per step ONE pass over the state
-// (force from the list + velocity-Verlet + energies + displacement test: each particle's state
-// is read once and written once) and one grid barrier; the rebuild (single-digit radix =
-// counting sort of cell ids, prefix sum, deterministic in-cell ordering, gather, list build)
-// runs inside the same kernel under a grid-uniform condition: no host round trip (MD:82,103).
+// Data layout in HBM (all in cell-sorted "slot" order; every row starts on an even slot, a row with
+// an odd population is padded with one sentinel slot, so slots pair up as aligned float2):
+//   X[2], Y[2]  float   positions, structure-of-arrays, ping-pong by step (the buffer being read is
+//                        never written in a step).  One 64-bit load = the x of two adjacent slots
+//                        = one operand of the packed FP32x2 pipe.
+//   V[2]        float2  velocities (buffers swap at a rebuild)
+//   orig[2]     int32   original particle index of each slot (-1 = pad)
+//   Rb          float2  positions at the last rebuild (max-displacement test against skin/2; also
+//                        gives the slot's cell, hence its three candidate ranges)
+//   cell_start  int32   prefix-sum cell index over nrows*nbx cells (+1)
+//
+// One PERSISTENT cooperative kernel runs a whole ljmd_run().  Per step ONE pass over the state
+// (each thread owns two adjacent slots: forces from the three ranges + velocity-Verlet + energies +
+// displacement test; state read once, written once) and one grid barrier.  The rebuild (bin +
+// histogram with rank capture -> row-structured prefix sum -> scatter -> deterministic in-cell
+// order by original index + gather) runs inside the same kernel under a grid-uniform condition:
+// no host round trip (MD:82,103).
 #include "ljmd_device.cuh"
 
 #include <algorithm>
@@ -31,26 +38,37 @@ namespace ljmd {
 
 namespace {
 
-constexpr int CL_THREADS  = 512;
-constexpr int CL_MAXN     = 64;    // list capacity per particle; 19.7 neighbours expected at rho 0.8
-constexpr int CL_BATCH    = 4;     // list words (= 8 neighbours) decoded and gathered together
-constexpr int CL_PREFETCH = 16;    // list words requested up-front per particle (32 neighbours)
-constexpr int CL_CELLCAP  = 16;    // in-register ordering of a cell's members (slow path beyond)
+constexpr int   CL_THREADS = 256;
+#ifndef LJMD_CELLS_MINBLOCKS
+#define LJMD_CELLS_MINBLOCKS 2
+#endif
+constexpr int   CL_MINBLOCKS = LJMD_CELLS_MINBLOCKS;
+constexpr int   CL_K       = 4;        // bins per (rc + skin)
+constexpr int   CL_ORDER_MAX = 64;     // cells denser than this keep arrival order (see B5)
+// Pad slots sit far outside any box, each at its OWN place (pad_x): two pads must never coincide,
+// because a zero r2 would poison its partner in the shared-reciprocal evaluation (0 * inf).
+// Squares and products of two squared distances stay far inside the fp32 range.
+constexpr float CL_SENT    = 1.0e8f;
 
-enum { ST_PR = 0, ST_PV = 1, ST_REBUILDS = 2, ST_ERR = 3, ST_FLAG = 4, ST_WORDS = 8 };
-enum { CERR_BARRIER = 1, CERR_LIST_OVERFLOW = 2 };
+#ifndef LJMD_CELLS_RCP_PRODUCT
+#define LJMD_CELLS_RCP_PRODUCT 1       // one MUFU.RCP per TWO pairs (1/(a*b) trick), see eval_set
+#endif
+
+enum { ST_PR = 0, ST_PV = 1, ST_REBUILDS = 2, ST_ERR = 3, ST_FLAG = 4, ST_NTOT = 5, ST_WORDS = 8 };
+enum { CERR_BARRIER = 1 };
 
 struct CellsArgs {
     PairConsts pc;
-    int   N, Npad, G, ncell, ncells;
-    float inv_cell, cell_size, rlist2, half_skin2, dt;
-    float2* Rs[2];
-    float2* Vh[2];
+    int   N, Nalloc, G;
+    int   nrows, nbx, ncells;
+    float inv_hy, inv_wx, half_skin2, dt;
+    float*  X[2];
+    float*  Y[2];
+    float2* V[2];
     int*    orig[2];
-    float2* Rbuild;
-    int *key, *slot_src, *cell_count, *cell_start, *fill, *chunk_tot;
-    unsigned* meta;
-    unsigned* nbr2;
+    float2* Rb;
+    float2* Fs;                     // forces held across the thermostat barrier
+    int *key, *rank, *tmp, *cell_count, *cell_start, *row_tot;
     float  *pe_part, *ke_part;      // [2*G]
     int*      state;                // ST_* words
     unsigned* bar;
@@ -66,10 +84,14 @@ struct CellsArgs {
     float   count_r2;
 };
 
-__device__ __forceinline__ int cell_coord(float x, float inv_cell, int ncell) {
-    // one fp32 multiply then truncation (x >= 0); the clamp handles x == box (MD:72 closed range)
-    int c = (int)(x * inv_cell);
-    return max(0, min(c, ncell - 1));
+__device__ __forceinline__ float pad_x(int row, int nrows) {
+    return CL_SENT * (1.0f + (float)row / (float)nrows);
+}
+
+// one fp32 multiply then truncation (x >= 0); the clamp handles x == box (MD:72 closed range)
+__device__ __forceinline__ int strip_coord(float x, float inv, int n) {
+    const int c = (int)(x * inv);
+    return max(0, min(c, n - 1));
 }
 
 // block-wide exclusive scan of one int per thread; returns the exclusive prefix, *total = block sum
@@ -102,7 +124,7 @@ __device__ __forceinline__ int block_exscan(int v, int* swarp /* CL_THREADS/32 +
 
 struct Ctx {
     unsigned epoch;
-    int pr, pv;
+    int pr, pv, ntot;
     long long* pt;      // shared-memory phase clocks (thread 0), or nullptr
 };
 
@@ -117,337 +139,387 @@ struct Ctx {
 
 #define CL_BARRIER() grid_barrier(a.bar, (++ctx.epoch) * (unsigned)a.G, a.state + ST_ERR)
 
-// The candidates of stencil row yy for a particle in cell column cx are the members of cells
-// cx-1, cx, cx+1 of that row: contiguous in sorted order, except that at the two edge columns
-// the wrapped cell sits at the other end of the row.  The window is therefore expressed in a
-// VIRTUAL index space (the row extended by one periodic copy on each side); to_real() folds a
-// virtual index back into the row.  Interior columns never need the fold.
-struct RowWin { int base, len, rstart, rlen; };
-
-__device__ __forceinline__ RowWin row_window(const int* __restrict__ cs, int nc, int cx, int yy) {
-    const int row0 = yy * nc;
-    RowWin w;
-    w.rstart = cs[row0];
-    w.rlen = cs[row0 + nc] - w.rstart;
-    int lo, hi;
-    if (cx == 0)           { lo = cs[row0 + nc - 1] - w.rlen; hi = cs[row0 + 2]; }
-    else if (cx == nc - 1) { lo = cs[row0 + nc - 2];          hi = cs[row0 + 1] + w.rlen; }
-    else                   { lo = cs[row0 + cx - 1];          hi = cs[row0 + cx + 2]; }
-    w.base = lo;
-    w.len = hi - lo;
-    return w;
-}
-__device__ __forceinline__ int to_real(int jv, int rstart, int rlen) {
-    jv += (jv < rstart) ? rlen : 0;
-    jv -= (jv >= rstart + rlen) ? rlen : 0;
-    return jv;
-}
-__device__ __forceinline__ int wrap_row(int y, int nc) {
-    y += (y < 0) ? nc : 0;
-    y -= (y >= nc) ? nc : 0;
-    return y;
-}
-
-// ---- rebuild: bin -> counting sort (radix 2^k single digit) -> prefix sum -> gather -> list ----
-__device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float rl2) {
+// ---- rebuild: counting sort by cell, row-structured index, deterministic in-cell order -----------
+__device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan) {
     const int tid = threadIdx.x, gtid = blockIdx.x * CL_THREADS + tid, gsz = a.G * CL_THREADS;
-    const float2* Rcur = a.Rs[ctx.pr];
+    const float* __restrict__ Xc = a.X[ctx.pr];
+    const float* __restrict__ Yc = a.Y[ctx.pr];
+    const int* __restrict__ orig_old = a.orig[ctx.pv];
+    const int ntot_old = ctx.ntot;
     CL_PROF(0);
-    // R1: clear per-cell counters
-    for (int c = gtid; c < a.ncells; c += gsz) { a.cell_count[c] = 0; a.fill[c] = 0; }
+    // B1: cell of every live slot + histogram; the atomic's return value is the slot's (arbitrary)
+    //     arrival rank inside its cell, so the scatter needs no second atomic pass.
+    //     (cell_count is all-zero on entry: cleared at create and again by B3 of every rebuild.)
+    for (int k = gtid; k < ntot_old; k += gsz) {
+        int c = -1;
+        if (orig_old[k] >= 0) {
+            c = strip_coord(Yc[k], a.inv_hy, a.nrows) * a.nbx + strip_coord(Xc[k], a.inv_wx, a.nbx);
+            a.rank[k] = atomicAdd(&a.cell_count[c], 1);
+        }
+        a.key[k] = c;
+    }
     CL_BARRIER();
     CL_PROF(2);
-    // R2: cell id of every particle (current order) + histogram
-    for (int k = gtid; k < a.N; k += gsz) {
-        const float2 r = Rcur[k];
-        const int c = cell_coord(r.y, a.inv_cell, a.ncell) * a.ncell + cell_coord(r.x, a.inv_cell, a.ncell);
-        a.key[k] = c;
-        atomicAdd(&a.cell_count[c], 1);
+    // B2: population of every row
+    for (int r = blockIdx.x; r < a.nrows; r += a.G) {
+        int s = 0;
+        for (int b = tid; b < a.nbx; b += CL_THREADS) s += a.cell_count[r * a.nbx + b];
+        int tot;
+        (void)block_exscan(s, sscan, &tot);
+        if (tid == 0) a.row_tot[r] = tot;
     }
     CL_BARRIER();
     CL_PROF(3);
-    // R3: prefix sum over cells.  pass 1: per-CTA chunk totals
-    const int chunk = (a.ncells + a.G - 1) / a.G;
-    const int c0 = min(a.ncells, blockIdx.x * chunk), c1 = min(a.ncells, c0 + chunk);
+    // B3: row offsets (every row starts on an even slot) + in-row exclusive scan -> cell_start;
+    //     an odd row gets one sentinel pad slot; the row's counters are cleared for the next rebuild.
     {
-        int s = 0;
-        for (int c = c0 + tid; c < c1; c += CL_THREADS) s += a.cell_count[c];
-        int tot;
-        (void)block_exscan(s, sscan, &tot);
-        if (tid == 0) a.chunk_tot[blockIdx.x] = tot;
+        float* Xn = a.X[ctx.pr ^ 1];
+        float* Yn = a.Y[ctx.pr ^ 1];
+        int* on = a.orig[ctx.pv ^ 1];
+        for (int r = blockIdx.x; r < a.nrows; r += a.G) {
+            int s = 0;
+            for (int q = tid; q < r; q += CL_THREADS) s += (a.row_tot[q] + 1) & ~1;
+            int carry;
+            (void)block_exscan(s, sscan, &carry);
+            const int rtot = a.row_tot[r];
+            const int row0 = carry;
+            for (int bb = 0; bb < a.nbx; bb += CL_THREADS) {
+                const int b = bb + tid;
+                int v = 0;
+                if (b < a.nbx) { v = a.cell_count[r * a.nbx + b]; a.cell_count[r * a.nbx + b] = 0; }
+                int tot;
+                const int ex = block_exscan(v, sscan, &tot);
+                if (b < a.nbx) a.cell_start[r * a.nbx + b] = carry + ex;
+                carry += tot;
+            }
+            if (tid == 0) {
+                if (rtot & 1) {
+                    const int pad = row0 + rtot;
+                    a.tmp[pad] = -1; on[pad] = -1;
+                    Xn[pad] = pad_x(r, a.nrows); Yn[pad] = CL_SENT;
+                    a.Rb[pad] = make_float2(CL_SENT, CL_SENT);
+                    a.V[ctx.pv ^ 1][pad] = make_float2(0.0f, 0.0f);
+                }
+                if (r == a.nrows - 1) a.cell_start[a.ncells] = row0 + ((rtot + 1) & ~1);
+            }
+        }
     }
     CL_BARRIER();
     CL_PROF(4);
-    //     pass 2: chunk offset + in-chunk exclusive scan -> cell_start
-    {
-        int s = 0;
-        for (int c = tid; c < blockIdx.x; c += CL_THREADS) s += a.chunk_tot[c];
-        int carry;
-        (void)block_exscan(s, sscan, &carry);
-        for (int cb = c0; cb < c1; cb += CL_THREADS) {
-            const int c = cb + tid;
-            const int v = (c < c1) ? a.cell_count[c] : 0;
-            int tot;
-            const int ex = block_exscan(v, sscan, &tot);
-            if (c < c1) a.cell_start[c] = carry + ex;
-            carry += tot;
-        }
-        if (blockIdx.x == a.G - 1 && tid == 0) a.cell_start[a.ncells] = a.N;
+    // B4: scatter source slots into their cell's range (arrival order inside a cell)
+    for (int k = gtid; k < ntot_old; k += gsz) {
+        const int c = a.key[k];
+        if (c >= 0) a.tmp[a.cell_start[c] + a.rank[k]] = k;
     }
     CL_BARRIER();
     CL_PROF(5);
-    // R5: scatter source indices into their cell's slot range (arbitrary order inside a cell)
-    for (int k = gtid; k < a.N; k += gsz) {
-        const int c = a.key[k];
-        const int slot = a.cell_start[c] + atomicAdd(&a.fill[c], 1);
-        a.slot_src[slot] = k;
-    }
-    CL_BARRIER();
-    CL_PROF(6);
-    // R6a: order every cell's members by ORIGINAL particle index => the sorted order (cell, orig)
-    //      is a pure function of the positions: bit-reproducible summation order downstream.
-    //      Rank by counting in registers (no data-dependent control flow) for cells up to
-    //      CL_CELLCAP members; insertion sort for the rare denser cell.
-    const int* orig_old = a.orig[ctx.pv];
-    for (int c = gtid; c < a.ncells; c += gsz) {
-        const int b = a.cell_start[c], e = a.cell_start[c + 1], n = e - b;
-        if (n <= 1) continue;
-        if (n <= CL_CELLCAP) {
-            int k[CL_CELLCAP], o[CL_CELLCAP];
-#pragma unroll
-            for (int p = 0; p < CL_CELLCAP; ++p) {
-                k[p] = (p < n) ? a.slot_src[b + p] : 0;
-                o[p] = (p < n) ? orig_old[k[p]] : 0x7fffffff;
-            }
-#pragma unroll
-            for (int p = 0; p < CL_CELLCAP; ++p) {
-                int rank = 0;
-#pragma unroll
-                for (int q = 0; q < CL_CELLCAP; ++q) rank += (o[q] < o[p]);
-                if (p < n) a.slot_src[b + rank] = k[p];
-            }
-        } else {
-            for (int p = b + 1; p < e; ++p) {
-                const int kp = a.slot_src[p], op = orig_old[kp];
-                int q = p - 1;
-                while (q >= b) {
-                    const int kq = a.slot_src[q];
-                    if (orig_old[kq] <= op) break;
-                    a.slot_src[q + 1] = kq;
-                    --q;
-                }
-                a.slot_src[q + 1] = kp;
-            }
-        }
-    }
-    CL_BARRIER();
-    CL_PROF(7);
-    // R6b: gather the state into the new order (coalesced writes)
+    // B5: each new slot picks the member of its cell whose ORIGINAL index has the slot's rank, so
+    //     the sorted order (cell, orig) is a pure function of the positions (bit-reproducible
+    //     summation order downstream), then gathers that member's state (coalesced writes).
+    //     (A bin holds ~1.6 particles at liquid density; a bin with more than CL_ORDER_MAX members
+    //     keeps its arrival order: still correct, no longer run-to-run bit-reproducible.)
     {
-        float2* Rn = a.Rs[ctx.pr ^ 1];
-        const float2* Vo = a.Vh[ctx.pv];
-        float2* Vn = a.Vh[ctx.pv ^ 1];
+        const int ntot_new = a.cell_start[a.ncells];
+        float* Xn = a.X[ctx.pr ^ 1];
+        float* Yn = a.Y[ctx.pr ^ 1];
+        const float2* Vo = a.V[ctx.pv];
+        float2* Vn = a.V[ctx.pv ^ 1];
         int* on = a.orig[ctx.pv ^ 1];
-        for (int i = gtid; i < a.N; i += gsz) {
-            const int k = a.slot_src[i];
-            const float2 r = Rcur[k];
-            Rn[i] = r;
-            a.Rbuild[i] = r;
-            Vn[i] = Vo[k];
-            on[i] = orig_old[k];
-            a.meta[i] = (unsigned)a.key[k];                 // cell id, replaced by count|edge in R7
+        for (int d = gtid; d < ntot_new; d += gsz) {
+            const int k = a.tmp[d];
+            if (k < 0) continue;                                  // pad slot (initialised in B3)
+            const int c = a.key[k];
+            const int b = a.cell_start[c], n = a.cell_start[c + 1] - b, p = d - b;
+            int ksel = k;
+            if (n > 1 && n <= CL_ORDER_MAX) {
+                for (int m = 0; m < n; ++m) {
+                    const int km = a.tmp[b + m];
+                    if (km < 0) continue;                         // the row's pad sits in its last bin
+                    const int om = orig_old[km];
+                    int rk = 0;
+                    for (int q = 0; q < n; ++q) {
+                        const int kq = a.tmp[b + q];
+                        rk += (kq >= 0 && orig_old[kq] < om);
+                    }
+                    if (rk == p) { ksel = km; break; }
+                }
+            }
+            const float x = Xc[ksel], y = Yc[ksel];
+            Xn[d] = x; Yn[d] = y;
+            a.Rb[d] = make_float2(x, y);
+            Vn[d] = Vo[ksel];
+            on[d] = orig_old[ksel];
         }
+        ctx.ntot = ntot_new;
     }
     ctx.pr ^= 1;
     ctx.pv ^= 1;
-    CL_BARRIER();
-    CL_PROF(8);
-    // R7: compressed Verlet list from the 3x3 stencil: r2 < rl2, j != i, with r2 the same unfused
-    //     fp32 expression as the oracle (bit-exact neighbour counts).  Warps whose particles all
-    //     sit in interior cells skip the min-image and the window fold (both are identities there).
-    {
-        const float2* __restrict__ R = a.Rs[ctx.pr];
-        const int* __restrict__ cs = a.cell_start;
-        const PairConsts pc = a.pc;
-        const int nc = a.ncell, N = a.N, halfN = a.N >> 1;
-        for (int base = blockIdx.x * CL_THREADS; base < a.Npad; base += gsz) {
-            const int  i = base + tid;
-            const bool live = i < N;
-            float2 ri = make_float2(0.0f, 0.0f);
-            int cx = 1, cy = 1;
-            if (live) {
-                ri = R[i];
-                const int c = (int)a.meta[i];
-                cy = c / nc; cx = c - cy * nc;
-            }
-            const bool edge = (cx == 0) | (cx == nc - 1) | (cy == 0) | (cy == nc - 1);
-            const bool wedge = __any_sync(0xffffffffu, edge);
-            int n = 0;
-            unsigned word = 0;
-            // append neighbour j (hit) to the packed list
-            auto push = [&](int dj) {
-                if (a.mode == 0 && n < CL_MAXN) {
-                    word |= ((unsigned)dj & 0xffffu) << (16 * (n & 1));
-                    if (n & 1) { a.nbr2[(size_t)(n >> 1) * a.Npad + i] = word; word = 0; }
-                }
-                ++n;
-            };
-            if (live) {
-#pragma unroll 1
-                for (int r = 0; r < 3 && wedge; ++r) {
-                    const int yy = wrap_row(cy + r - 1, nc);
-                    {
-                        const RowWin w = row_window(cs, nc, cx, yy);
-#pragma unroll 1
-                        for (int k0 = 0; k0 < w.len; k0 += 4) {
-                            int jj[4]; float2 rj[4];
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {          // 4 independent loads in flight
-                                jj[t] = to_real(w.base + min(k0 + t, w.len - 1), w.rstart, w.rlen);
-                                rj[t] = R[jj[t]];
-                            }
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                const float dx = min_image(__fsub_rn(ri.x, rj[t].x), pc.box, pc.timg);
-                                const float dy = min_image(__fsub_rn(ri.y, rj[t].y), pc.box, pc.timg);
-                                const float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-                                if (k0 + t < w.len && jj[t] != i && r2 < rl2) {
-                                    int dj = jj[t] - i;                    // fold modulo N into +-N/2
-                                    dj += (dj < -halfN) ? N : 0;
-                                    dj -= (dj > halfN) ? N : 0;
-                                    push(dj);
-                                }
-                            }
-                        }
-                    }
-                }
-                if (!wedge) {
-                    // interior: the three row windows are plain contiguous ranges; walk them as one
-                    // flattened candidate sequence with 8 position loads in flight
-                    int jlo[3], len[3];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        const int row0 = (cy + r - 1) * nc + cx;
-                        jlo[r] = cs[row0 - 1];
-                        len[r] = cs[row0 + 2] - jlo[r];
-                    }
-                    const int e0 = len[0], e1 = len[0] + len[1], tot = e1 + len[2];
-                    const int d1 = jlo[1] - e0, d2 = jlo[2] - e1;
-#pragma unroll 1
-                    for (int cb = 0; cb < tot; cb += 8) {
-                        int jj[8]; float2 rj[8];
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            const int c = min(cb + t, tot - 1);
-                            jj[t] = c + ((c < e0) ? jlo[0] : ((c < e1) ? d1 : d2));
-                            rj[t] = R[jj[t]];
-                        }
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            const float dx = __fsub_rn(ri.x, rj[t].x), dy = __fsub_rn(ri.y, rj[t].y);
-                            const float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-                            if (cb + t < tot && jj[t] != i && r2 < rl2) push(jj[t] - i);
-                        }
-                    }
-                }
-            }
-            if (a.mode == 0) {
-                // the force pass walks every lane to the warp's longest list, in batches of
-                // CL_BATCH words: pad the shorter lists with dj = 0 (the particle itself, which
-                // the keep predicate masks) so that decode needs no bounds handling.
-                int nmax = min(n, CL_MAXN);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
-                if (live) {
-                    const int nw_pad = min(CL_MAXN / 2, (((nmax + 1) >> 1) + CL_BATCH - 1) / CL_BATCH * CL_BATCH);
-                    int wdone = min(n, CL_MAXN) >> 1;
-                    if ((n & 1) && n < CL_MAXN) { a.nbr2[(size_t)wdone * a.Npad + i] = word; ++wdone; }
-                    for (int u = wdone; u < nw_pad; ++u) a.nbr2[(size_t)u * a.Npad + i] = 0u;
-                    if (n > CL_MAXN) atomicOr(a.state + ST_ERR, CERR_LIST_OVERFLOW);
-                    a.meta[i] = (unsigned)min(n, CL_MAXN) | (edge ? 0x100u : 0u);
-                }
-            } else if (live) {
-                a.key[i] = n;                   // count mode: full count, nothing stored
-            }
-        }
-    }
     if (blockIdx.x == 0 && tid == 0) a.state[ST_REBUILDS] += 1;
     CL_BARRIER();
-    CL_PROF(9);
+    CL_PROF(6);
 }
 
-// ---- per-step pass: list force for one particle ----------------------------------------------------
-// EDGE: the warp contains a particle of a boundary cell => min-image and the modulo-N index fold
-// are applied; interior warps skip both (|d| << box/2 for every listed neighbour).
-// The particle's list words are fetched 8 at a time (16 neighbours in flight) before any gather.
-template <bool PE, bool EDGE>
-__device__ __forceinline__ void pair_list(const PairConsts& pc, float2 ri, float2 rj, bool keep,
-                                          float& fx, float& fy, float& pe) {
-    float dx = __fsub_rn(ri.x, rj.x), dy = __fsub_rn(ri.y, rj.y);
-    if (EDGE) { dx = min_image(dx, pc.box, pc.timg); dy = min_image(dy, pc.box, pc.timg); }
-    const float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-    float ir2 = rcp_approx(r2);
-    ir2 = (keep & (r2 < pc.rc2)) ? ir2 : 0.0f;
-    const float ir6 = ir2 * ir2 * ir2;
-    const float f = fmaf(ir6, pc.c12, -pc.c6) * (ir6 * ir2);
-    fx = fmaf(f, dx, fx);
-    fy = fmaf(f, dy, fy);
-    if (PE) pe = fmaf(ir6, fmaf(ir6, pc.d12, -pc.d6), pe);
-}
-
-template <bool PE, bool EDGE>
-__device__ __forceinline__ void list_batch(const PairConsts& pc, const float2* __restrict__ R, int i,
-                                           int N, float2 ri, int n, int s0, const unsigned (&w)[CL_BATCH],
-                                           float& fx, float& fy, float& pe) {
-    int    j[2 * CL_BATCH];
-    float2 rj[2 * CL_BATCH];
-#pragma unroll
-    for (int u = 0; u < CL_BATCH; ++u) {
-        j[2 * u]     = i + (int)(short)(w[u] & 0xffffu);
-        j[2 * u + 1] = i + ((int)w[u] >> 16);
+// ---- packed pair evaluation ------------------------------------------------------------------------
+// A thread owns the adjacent slots i0 = 2p, i1 = 2p+1 (packed as xi2 = (x_i0, x_i1)).  One iteration
+// loads the x and y of the two adjacent candidate slots j0 = 2m, j1 = 2m+1 as two 64-bit loads and
+// evaluates FOUR pairs on the packed FP32x2 pipe with no register shuffling:
+//   "straight" set (i0,j0),(i1,j1) from xi2, "swapped" set (i1,j0),(i0,j1) from the swapped copy
+//   (x_i1, x_i0) (an operand swizzle of FADD2, not a register move).
+// d is formed as xj - xi (= -(xi - xj) exactly), so the accumulators hold -F bit for bit.
+//   r2 = dx*dx + dy*dy unfused (fma(t, 1, u) with a run-time 1: see pair2_accum) => the pair set
+//   {r2 < rc2} is the oracle's.
+//   LJMD_CELLS_RCP_PRODUCT: 1/r2 of the two pairs of a set from ONE MUFU.RCP of the product
+//   (ir2_a = r2_b * rcp(r2_a * r2_b)): MUFU issues at 1/8 rate and would otherwise co-limit the loop.
+// MODE 0: interior ranges of the rows above/below: no self pair possible, cutoff mask is a 1.0/0.0
+//         multiply (FSET + FMUL2).
+// MODE 1: interior range of the particle's own row: the straight set at m == p is the self pair,
+//         masked by select (which also discards the NaN of 0 * inf).
+// MODE 2: edge warps: exact minimum image on every displacement and per-pair keep predicates
+//         (exact range bounds, general self test).
+template <bool PE, int MODE>
+__device__ __forceinline__ void eval_set(const PairConsts& pc, const PairConsts2& c2, float2 nxi,
+                                         float2 nyi, float2 xj, float2 yj, bool keepx, bool keepy,
+                                         float2& ax, float2& ay, float2& pe2) {
+    float2 dx = __fadd2_rn(xj, nxi);
+    float2 dy = __fadd2_rn(yj, nyi);
+    if (MODE == 2) {
+        dx.x = min_image(dx.x, pc.box, pc.timg); dx.y = min_image(dx.y, pc.box, pc.timg);
+        dy.x = min_image(dy.x, pc.box, pc.timg); dy.y = min_image(dy.y, pc.box, pc.timg);
     }
-#pragma unroll
-    for (int t = 0; t < 2 * CL_BATCH; ++t) {
-        if (EDGE) { j[t] += (j[t] < 0) ? N : 0; j[t] -= (j[t] >= N) ? N : 0; }
-        rj[t] = R[j[t]];                            // all gathers of the batch in flight together
+    const float2 r2 = __ffma2_rn(__fmul2_rn(dx, dx), c2.one, __fmul2_rn(dy, dy));
+    float2 ir2;
+    if (MODE == 0) {
+        const float2 msk = make_float2((r2.x < pc.rc2) ? 1.0f : 0.0f, (r2.y < pc.rc2) ? 1.0f : 0.0f);
+#if LJMD_CELLS_RCP_PRODUCT
+        const float rp = rcp_approx(__fmul_rn(r2.x, r2.y));
+        ir2 = __fmul2_rn(__fmul2_rn(make_float2(r2.y, r2.x), msk), make_float2(rp, rp));
+#else
+        ir2 = __fmul2_rn(make_float2(rcp_approx(r2.x), rcp_approx(r2.y)), msk);
+#endif
+    } else {
+#if LJMD_CELLS_RCP_PRODUCT
+        const float rp = rcp_approx(__fmul_rn(r2.x, r2.y));
+        ir2 = make_float2(__fmul_rn(r2.y, rp), __fmul_rn(r2.x, rp));
+#else
+        ir2 = make_float2(rcp_approx(r2.x), rcp_approx(r2.y));
+#endif
+        ir2.x = (keepx & (r2.x < pc.rc2)) ? ir2.x : 0.0f;
+        ir2.y = (keepy & (r2.y < pc.rc2)) ? ir2.y : 0.0f;
     }
-#pragma unroll
-    for (int t = 0; t < 2 * CL_BATCH; ++t)
-        pair_list<PE, EDGE>(pc, ri, rj[t], (s0 + t) < n, fx, fy, pe);
+    const float2 ir6 = __fmul2_rn(__fmul2_rn(ir2, ir2), ir2);
+    const float2 f = __fmul2_rn(__ffma2_rn(ir6, c2.c12, c2.nc6), __fmul2_rn(ir6, ir2));
+    ax = __ffma2_rn(f, dx, ax);
+    ay = __ffma2_rn(f, dy, ay);
+    if (PE) pe2 = __ffma2_rn(ir6, __ffma2_rn(ir6, c2.d12, c2.nd6), pe2);
 }
 
-// All list words of the particle (up to CL_PREFETCH) are requested in ONE burst before any of
-// them is decoded: the pass is latency-bound otherwise (one HBM round trip per batch).
-template <bool PE, bool EDGE>
-__device__ __forceinline__ void list_force(const CellsArgs& a, const float2* __restrict__ R, int i,
-                                           float2 ri, int n, int nmax, float& fx, float& fy,
-                                           float& pe) {
+struct PairAcc {
+    float2 axA, ayA, axB, ayB, peA, peB;
+};
+
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// interior: slots [2*m0, 2*m1) (range aligned outwards to slot pairs: the extra slots belong to the
+// same row and to bins outside the stencil, hence beyond rc, and to no other range of this thread)
+template <bool PE, bool SELF>
+__device__ __forceinline__ void row_range(const PairConsts& pc, const PairConsts2& c2,
+                                          const float2* __restrict__ X2, const float2* __restrict__ Y2,
+                                          int m0, int m1, int p, float2 nxi, float2 nyi, float2 nxs,
+                                          float2 nys, PairAcc& acc) {
+#pragma unroll 2
+    for (int m = m0; m < m1; ++m) {
+        const float2 xj = X2[m], yj = Y2[m];
+        const bool k = (m != p);
+        eval_set<PE, SELF ? 1 : 0>(pc, c2, nxi, nyi, xj, yj, k, k, acc.axA, acc.ayA, acc.peA);
+        eval_set<PE, 0>(pc, c2, nxs, nys, xj, yj, true, true, acc.axB, acc.ayB, acc.peB);
+    }
+}
+
+// edge: slots [s, e) exactly, minimum image, any candidate may be one of the thread's own slots
+template <bool PE>
+__device__ __forceinline__ void edge_range(const PairConsts& pc, const PairConsts2& c2,
+                                           const float2* __restrict__ X2, const float2* __restrict__ Y2,
+                                           int s, int e, int p, float2 nxi, float2 nyi, float2 nxs,
+                                           float2 nys, PairAcc& acc) {
+    for (int m = s >> 1; m < ((e + 1) >> 1); ++m) {
+        const float2 xj = X2[m], yj = Y2[m];
+        const bool v0 = (2 * m >= s), v1 = (2 * m + 1 < e), own = (m == p);
+        eval_set<PE, 2>(pc, c2, nxi, nyi, xj, yj, v0 & !own, v1 & !own, acc.axA, acc.ayA, acc.peA);
+        eval_set<PE, 2>(pc, c2, nxs, nys, xj, yj, v0, v1, acc.axB, acc.ayB, acc.peB);
+    }
+}
+
+// ---- scalar path (count mode only) ---------------------------------------------------------------
+// One particle against bins [b-K, b+K] of rows r-1, r, r+1 with periodic wrap of both indices: up to
+// two pieces per row, exact bounds, scalar arithmetic with the exact minimum image.
+template <bool PE, bool COUNT>
+__device__ __forceinline__ void generic_particle(const CellsArgs& a, const float* __restrict__ X,
+                                                 const float* __restrict__ Y, int i, float xi, float yi,
+                                                 int r, int b, float lim2, float& fx, float& fy,
+                                                 float& pe, int& cnt) {
     const PairConsts pc = a.pc;
-    const unsigned* __restrict__ np = a.nbr2 + i;
-    const size_t stride = (size_t)a.Npad;
-    const int nw = (nmax + 1) >> 1;                 // warp-uniform; lists are zero-padded to a batch
-    const int N = a.N;
-    unsigned w[CL_PREFETCH];
-#pragma unroll
-    for (int u = 0; u < CL_PREFETCH; ++u) w[u] = (u < nw) ? np[(size_t)u * stride] : 0u;
-#pragma unroll
-    for (int u0 = 0; u0 < CL_PREFETCH; u0 += CL_BATCH) {
-        if (u0 < nw) {                              // warp-uniform
-            unsigned wb[CL_BATCH];
-#pragma unroll
-            for (int u = 0; u < CL_BATCH; ++u) wb[u] = w[u0 + u];
-            list_batch<PE, EDGE>(pc, R, i, N, ri, n, 2 * u0, wb, fx, fy, pe);
+    const int* __restrict__ cs = a.cell_start;
+    for (int dr = -1; dr <= 1; ++dr) {
+        int rr = r + dr;
+        rr += (rr < 0) ? a.nrows : 0;
+        rr -= (rr >= a.nrows) ? a.nrows : 0;
+        const int lo = b - CL_K, hi = b + CL_K;
+        for (int piece = 0; piece < 3; ++piece) {
+            int bl, bh;
+            if (piece == 0)      { bl = max(lo, 0); bh = min(hi, a.nbx - 1); }
+            else if (piece == 1) { if (lo >= 0) continue; bl = lo + a.nbx; bh = a.nbx - 1; }
+            else                 { if (hi < a.nbx) continue; bl = 0; bh = hi - a.nbx; }
+            const int s = cs[rr * a.nbx + bl], e = cs[rr * a.nbx + bh + 1];
+            for (int j = s; j < e; ++j) {
+                if (j == i) continue;
+                const float xj = X[j], yj = Y[j];
+                if (COUNT) {
+                    const float dx = min_image(__fsub_rn(xi, xj), pc.box, pc.timg);
+                    const float dy = min_image(__fsub_rn(yi, yj), pc.box, pc.timg);
+                    const float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                    cnt += (r2 < lim2);
+                } else {
+                    pair_accum<true, PE, false>(xi, yi, xj, yj, true, pc, fx, fy, pe);
+                }
+            }
         }
     }
-    for (int u0 = CL_PREFETCH; u0 < nw; u0 += CL_BATCH) {     // rare: more than 2*CL_PREFETCH neighbours
-        unsigned wb[CL_BATCH];
-#pragma unroll
-        for (int u = 0; u < CL_BATCH; ++u) wb[u] = np[(size_t)(u0 + u) * stride];
-        list_batch<PE, EDGE>(pc, R, i, N, ri, n, 2 * u0, wb, fx, fy, pe);
+}
+
+// velocity-Verlet epilogue of one particle (MD:70-74) + outputs; returns "left the skin/2 ball"
+struct StepFlags {
+    bool kick1, final, want_e, thermo, sample;
+    long long s;
+};
+
+__device__ __forceinline__ bool finish_particle(const CellsArgs& a, const StepFlags& f, int slot, int o,
+                                                float rx, float ry, float Fx, float Fy, float2& v,
+                                                float2 rb, float& xn, float& yn, float& ke_thread) {
+    const RunCtl& rc = a.rc;
+    xn = rx; yn = ry;
+    if (f.kick1) { v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt); }                      // MD:74
+    if (f.want_e || f.thermo) ke_thread += v.x * v.x + v.y * v.y;
+    if (f.sample) rc.traj[(size_t)(f.s / rc.sample_every) * a.N + o] = make_float2(rx, ry);      // MD:93-100
+    if (f.thermo) {
+        a.Fs[slot] = make_float2(Fx, Fy);
+        return false;
+    }
+    if (f.final) {
+        if (a.R_out) a.R_out[o] = make_float2(rx, ry);
+        if (a.V_out) a.V_out[o] = v;
+        if (a.F_out) a.F_out[o] = make_float2(Fx, Fy);
+        return false;
+    }
+    v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt);                                        // MD:70
+    xn = drift(rx, v.x, a.dt, a.pc.box);                                                         // MD:71-72
+    yn = drift(ry, v.y, a.dt, a.pc.box);
+    const float ddx = min_image(__fsub_rn(xn, rb.x), a.pc.box, a.pc.timg);
+    const float ddy = min_image(__fsub_rn(yn, rb.y), a.pc.box, a.pc.timg);
+    return ddx * ddx + ddy * ddy > a.half_skin2;
+}
+
+template <bool PE>
+__device__ __forceinline__ void force_pass(const CellsArgs& a, const Ctx& ctx, const StepFlags& fl,
+                                           float& pe_thread, float& ke_thread, int& moved) {
+    const int tid = threadIdx.x, gsz = a.G * CL_THREADS;
+    const PairConsts pc = a.pc;
+    const PairConsts2 c2 = make_pair_consts2(pc);
+    const float* __restrict__ X = a.X[ctx.pr];
+    const float* __restrict__ Y = a.Y[ctx.pr];
+    const float2* __restrict__ X2 = reinterpret_cast<const float2*>(X);
+    const float2* __restrict__ Y2 = reinterpret_cast<const float2*>(Y);
+    float2* Xn2 = reinterpret_cast<float2*>(a.X[ctx.pr ^ 1]);
+    float2* Yn2 = reinterpret_cast<float2*>(a.Y[ctx.pr ^ 1]);
+    float4* V4 = reinterpret_cast<float4*>(a.V[ctx.pv]);
+    const float4* __restrict__ Rb4 = reinterpret_cast<const float4*>(a.Rb);
+    const int2* __restrict__ og2 = reinterpret_cast<const int2*>(a.orig[ctx.pv]);
+    const int* __restrict__ cs = a.cell_start;
+    const int npairs = ctx.ntot >> 1;
+    const int npad = (npairs + 31) & ~31;
+
+    for (int base = blockIdx.x * CL_THREADS; base < npad; base += gsz) {
+        const int  p = base + tid;
+        const bool act = p < npairs;
+        float2 xi = make_float2(CL_SENT, CL_SENT), yi = xi;
+        float4 rb = make_float4(CL_SENT, CL_SENT, CL_SENT, CL_SENT);
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        int2 o = make_int2(-1, -1);
+        if (act) {
+            xi = X2[p]; yi = Y2[p]; rb = Rb4[p]; o = og2[p];
+            if (a.rc.nsteps > 0) v = V4[p];
+        }
+        const bool live0 = o.x >= 0, live1 = o.y >= 0;
+        int r = 1, b0 = CL_K, b1 = CL_K;
+        if (live0) {
+            r  = strip_coord(rb.y, a.inv_hy, a.nrows);
+            b0 = strip_coord(rb.x, a.inv_wx, a.nbx);
+            b1 = live1 ? strip_coord(rb.z, a.inv_wx, a.nbx) : b0;
+        }
+        const bool edge = (r == 0) | (r == a.nrows - 1) | (b0 < CL_K) | (b1 > a.nbx - 1 - CL_K);
+        const bool wedge = __any_sync(0xffffffffu, edge);
+        float F0x = 0.0f, F0y = 0.0f, F1x = 0.0f, F1y = 0.0f;
+        {
+            PairAcc acc;
+            acc.axA = acc.ayA = acc.axB = acc.ayB = acc.peA = acc.peB = make_float2(0.0f, 0.0f);
+            const float2 nxi = make_float2(-xi.x, -xi.y), nyi = make_float2(-yi.x, -yi.y);
+            const float2 nxs = make_float2(-xi.y, -xi.x), nys = make_float2(-yi.y, -yi.x);
+            if (!wedge) {
+                if (live0) {
+                    const int cl = r * a.nbx + b0 - CL_K, ch = r * a.nbx + b1 + CL_K + 1;
+                    const int s0 = cs[cl - a.nbx], e0 = cs[ch - a.nbx];
+                    const int s1 = cs[cl],         e1 = cs[ch];
+                    const int s2 = cs[cl + a.nbx], e2 = cs[ch + a.nbx];
+                    // the own row and the row below are needed ~1000 issue slots from now: start
+                    // their lines on the way to L1 while the first range is evaluated
+                    prefetch_l1(X2 + (s1 >> 1)); prefetch_l1(Y2 + (s1 >> 1));
+                    prefetch_l1(X2 + (e1 >> 1)); prefetch_l1(Y2 + (e1 >> 1));
+                    prefetch_l1(X2 + (s2 >> 1)); prefetch_l1(Y2 + (s2 >> 1));
+                    prefetch_l1(X2 + (e2 >> 1)); prefetch_l1(Y2 + (e2 >> 1));
+                    row_range<PE, false>(pc, c2, X2, Y2, s0 >> 1, (e0 + 1) >> 1, p, nxi, nyi, nxs, nys, acc);
+                    row_range<PE, true >(pc, c2, X2, Y2, s1 >> 1, (e1 + 1) >> 1, p, nxi, nyi, nxs, nys, acc);
+                    row_range<PE, false>(pc, c2, X2, Y2, s2 >> 1, (e2 + 1) >> 1, p, nxi, nyi, nxs, nys, acc);
+                }
+            } else if (live0) {
+                // bins [b0-K, b1+K] of rows r-1, r, r+1 with periodic wrap of both indices: one piece
+                // plus up to two wrapped pieces per row (the whole row once if the union would overlap)
+                int lo = b0 - CL_K, hi = b1 + CL_K;
+                if (hi - lo + 1 > a.nbx) { lo = 0; hi = a.nbx - 1; }
+#pragma unroll 1
+                for (int dr = -1; dr <= 1; ++dr) {
+                    int rr = r + dr;
+                    rr += (rr < 0) ? a.nrows : 0;
+                    rr -= (rr >= a.nrows) ? a.nrows : 0;
+                    const int* __restrict__ csr = cs + rr * a.nbx;
+#pragma unroll 1
+                    for (int piece = 0; piece < 3; ++piece) {
+                        int bl, bh;
+                        if (piece == 0)      { bl = max(lo, 0); bh = min(hi, a.nbx - 1); }
+                        else if (piece == 1) { if (lo >= 0) continue; bl = lo + a.nbx; bh = a.nbx - 1; }
+                        else                 { if (hi < a.nbx) continue; bl = 0; bh = hi - a.nbx; }
+                        edge_range<PE>(pc, c2, X2, Y2, csr[bl], csr[bh + 1], p, nxi, nyi, nxs, nys, acc);
+                    }
+                }
+            }
+            // accumulators hold -F:  i0 <- straight.x + swapped.y,  i1 <- straight.y + swapped.x
+            F0x = -(acc.axA.x + acc.axB.y); F0y = -(acc.ayA.x + acc.ayB.y);
+            F1x = -(acc.axA.y + acc.axB.x); F1y = -(acc.ayA.y + acc.ayB.x);
+            if (PE) pe_thread += (acc.peA.x + acc.peB.y) + (acc.peA.y + acc.peB.x);
+        }
+        if (!act) continue;
+        float2 v0 = make_float2(v.x, v.y), v1 = make_float2(v.z, v.w);
+        float2 xn = xi, yn = yi;
+        if (live0) moved |= finish_particle(a, fl, 2 * p, o.x, xi.x, yi.x, F0x, F0y, v0, make_float2(rb.x, rb.y), xn.x, yn.x, ke_thread);
+        if (live1) moved |= finish_particle(a, fl, 2 * p + 1, o.y, xi.y, yi.y, F1x, F1y, v1, make_float2(rb.z, rb.w), xn.y, yn.y, ke_thread);
+        if (a.rc.nsteps > 0 && !(fl.final && !fl.thermo)) {
+            V4[p] = make_float4(v0.x, v0.y, v1.x, v1.y);
+            if (!fl.thermo) { Xn2[p] = xn; Yn2[p] = yn; }
+        }
     }
 }
 
-__global__ void __launch_bounds__(CL_THREADS, 2)
+__global__ void __launch_bounds__(CL_THREADS, CL_MINBLOCKS)
 cells_persistent_kernel(const CellsArgs a) {
     __shared__ int   sscan[CL_THREADS / 32 + 1];
     __shared__ float sred[CL_THREADS / 32];
@@ -461,103 +533,70 @@ cells_persistent_kernel(const CellsArgs a) {
     if (ctx.pt && tid == 0) { for (int k = 0; k < 11; ++k) s_pt[k] = 0; s_pt[11] = clock64(); }
     ctx.pr = a.state[ST_PR];
     ctx.pv = a.state[ST_PV];
+    ctx.ntot = a.state[ST_NTOT];
 
     if (a.s_begin < 0) {
-        // load the caller's state (original order) and build the first list
+        // load the caller's state (original order, no pads) and sort it
         for (int i = gtid; i < a.N; i += gsz) {
-            a.Rs[ctx.pr][i] = a.R_in[i];
-            a.Vh[ctx.pv][i] = a.V_in ? a.V_in[i] : make_float2(0.0f, 0.0f);
+            const float2 r = a.R_in[i];
+            a.X[ctx.pr][i] = r.x;
+            a.Y[ctx.pr][i] = r.y;
+            a.V[ctx.pv][i] = a.V_in ? a.V_in[i] : make_float2(0.0f, 0.0f);
             a.orig[ctx.pv][i] = i;
         }
+        ctx.ntot = a.N;
         CL_BARRIER();
-        cells_rebuild(a, ctx, sscan, (a.mode == 1) ? a.count_r2 : a.rlist2);
+        cells_rebuild(a, ctx, sscan);
         if (a.mode == 1) {
+            // neighbour recount through the same ranges (generic path), original order out
+            const float* X = a.X[ctx.pr];
+            const float* Y = a.Y[ctx.pr];
             const int* og = a.orig[ctx.pv];
-            for (int i = gtid; i < a.N; i += gsz) a.count_out[og[i]] = a.key[i];
-            if (gtid == 0) { a.state[ST_PR] = ctx.pr; a.state[ST_PV] = ctx.pv; }
+            for (int i = gtid; i < ctx.ntot; i += gsz) {
+                const int o = og[i];
+                if (o < 0) continue;
+                const float xi = X[i], yi = Y[i];
+                float fx = 0.0f, fy = 0.0f, pe = 0.0f;
+                int cnt = 0;
+                generic_particle<false, true>(a, X, Y, i, xi, yi, strip_coord(yi, a.inv_hy, a.nrows),
+                                              strip_coord(xi, a.inv_wx, a.nbx), a.count_r2, fx, fy, pe, cnt);
+                a.count_out[o] = cnt;
+            }
+            if (gtid == 0) { a.state[ST_PR] = ctx.pr; a.state[ST_PV] = ctx.pv; a.state[ST_NTOT] = ctx.ntot; }
             return;
         }
     }
 
     for (long long s = a.s_begin; s < a.s_end; ++s) {
-        const int  par     = (int)((s + 1) & 1);
-        const bool kick1   = (s >= 0);
-        const bool final   = (s == rc.nsteps - 1);
-        const bool want_e  = kick1 && rc.energy_every > 0 && (s % rc.energy_every == 0);
-        const bool want_pe = want_e || (rc.nsteps == 0 && a.pe_out != nullptr);
-        const bool thermo  = kick1 && rc.thermo_every > 0 && rc.thermo_kT > 0.0f &&
-                             ((s + 1) % rc.thermo_every == 0);
-        const bool sample  = kick1 && rc.sample_every > 0 && (s % rc.sample_every == 0) &&
-                             (s / rc.sample_every < rc.S);
+        const int par = (int)((s + 1) & 1);
+        StepFlags fl;
+        fl.s      = s;
+        fl.kick1  = (s >= 0);
+        fl.final  = (s == rc.nsteps - 1);
+        fl.want_e = fl.kick1 && rc.energy_every > 0 && (s % rc.energy_every == 0);
+        const bool want_pe = fl.want_e || (rc.nsteps == 0 && a.pe_out != nullptr);
+        fl.thermo = fl.kick1 && rc.thermo_every > 0 && rc.thermo_kT > 0.0f &&
+                    ((s + 1) % rc.thermo_every == 0);
+        fl.sample = fl.kick1 && rc.sample_every > 0 && (s % rc.sample_every == 0) &&
+                    (s / rc.sample_every < rc.S);
         // rebuild requested by the previous step's displacement test?
         if (s > a.s_begin || a.s_begin >= 0) {
-            if (__ldcg(a.state + ST_FLAG) == (int)(s + 1)) cells_rebuild(a, ctx, sscan, a.rlist2);
+            if (__ldcg(a.state + ST_FLAG) == (int)(s + 1)) cells_rebuild(a, ctx, sscan);
         }
-        const float2* __restrict__ R = a.Rs[ctx.pr];
-        float2*       Rnext = a.Rs[ctx.pr ^ 1];
-        float2*       Vh    = a.Vh[ctx.pv];
-        const int*    og    = a.orig[ctx.pv];
-
         float ke_thread = 0.0f, pe_thread = 0.0f;
         int   moved = 0;
-        for (int base = blockIdx.x * CL_THREADS; base < a.Npad; base += gsz) {
-            const int  i    = base + tid;
-            const bool live = i < a.N;
-            float2 ri = make_float2(0.0f, 0.0f);
-            unsigned meta = 0u;                         // dead lanes: interior, no neighbours
-            if (live) { ri = R[i]; meta = a.meta[i]; }
-            const int n = meta & 0xff;
-            int nmax = n;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
-            const bool wedge = __any_sync(0xffffffffu, (meta & 0x100u) != 0u);
-            float Fx = 0.0f, Fy = 0.0f, pe = 0.0f;
-            const int ii = live ? i : 0;
-            // epilogue operands requested now, consumed after the force loop
-            float2 v = make_float2(0.0f, 0.0f), rb = make_float2(0.0f, 0.0f);
-            if (live && rc.nsteps > 0) { v = Vh[i]; rb = a.Rbuild[i]; }
-            if (want_pe) {
-                if (wedge) list_force<true, true >(a, R, ii, ri, n, nmax, Fx, Fy, pe);
-                else       list_force<true, false>(a, R, ii, ri, n, nmax, Fx, Fy, pe);
-            } else {
-                if (wedge) list_force<false, true >(a, R, ii, ri, n, nmax, Fx, Fy, pe);
-                else       list_force<false, false>(a, R, ii, ri, n, nmax, Fx, Fy, pe);
-            }
-            if (!live) continue;
-            pe_thread += pe;
-            if (kick1) { v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt); }            // MD:74
-            if (want_e || thermo) ke_thread += v.x * v.x + v.y * v.y;
-            const int o = (sample || final) ? og[i] : 0;
-            if (sample) rc.traj[(size_t)(s / rc.sample_every) * a.N + o] = ri;              // MD:93-100
-            if (thermo) {
-                Vh[i] = v;
-                a.Rbuild[a.Npad + i] = make_float2(Fx, Fy);     // scratch half of Rbuild: F across barrier
-                continue;
-            }
-            if (final) {
-                if (a.R_out) a.R_out[o] = ri;
-                if (a.V_out) a.V_out[o] = v;
-                if (a.F_out) a.F_out[o] = make_float2(Fx, Fy);
-            } else {
-                v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt);                         // MD:70
-                Vh[i] = v;
-                const float2 rn = make_float2(drift(ri.x, v.x, a.dt, a.pc.box),               // MD:71-72
-                                              drift(ri.y, v.y, a.dt, a.pc.box));
-                Rnext[i] = rn;
-                const float ddx = min_image(__fsub_rn(rn.x, rb.x), a.pc.box, a.pc.timg);
-                const float ddy = min_image(__fsub_rn(rn.y, rb.y), a.pc.box, a.pc.timg);
-                moved |= (ddx * ddx + ddy * ddy > a.half_skin2);
-            }
-        }
+        if (want_pe) force_pass<true >(a, ctx, fl, pe_thread, ke_thread, moved);
+        else         force_pass<false>(a, ctx, fl, pe_thread, ke_thread, moved);
+
         if (want_pe) {
             float t = block_sum<CL_THREADS>(pe_thread, sred);
             if (tid == 0) __stcg(&a.pe_part[par * a.G + blockIdx.x], t);
         }
-        if (want_e || thermo) {
+        if (fl.want_e || fl.thermo) {
             float t = block_sum<CL_THREADS>(ke_thread, sred);
             if (tid == 0) __stcg(&a.ke_part[par * a.G + blockIdx.x], t);
         }
-        if (thermo) {
+        if (fl.thermo) {
             CL_BARRIER();
             if (tid < 32) {
                 double ke2 = 0.0;
@@ -567,25 +606,31 @@ cells_persistent_kernel(const CellsArgs a) {
             }
             __syncthreads();
             const float lam = s_lambda;
-            for (int i = gtid; i < a.N; i += gsz) {
-                const float2 ri = R[i];
-                const float2 F = a.Rbuild[a.Npad + i];
-                float2 v = Vh[i];
+            const float* X = a.X[ctx.pr];
+            const float* Y = a.Y[ctx.pr];
+            float* Xn = a.X[ctx.pr ^ 1];
+            float* Yn = a.Y[ctx.pr ^ 1];
+            float2* V = a.V[ctx.pv];
+            const int* og = a.orig[ctx.pv];
+            for (int i = gtid; i < ctx.ntot; i += gsz) {
+                const int o = og[i];
+                if (o < 0) { if (!fl.final) { Xn[i] = X[i]; Yn[i] = Y[i]; } continue; }   // pad stays put
+                const float rx = X[i], ry = Y[i];
+                const float2 F = a.Fs[i];
+                float2 v = V[i];
                 v.x *= lam; v.y *= lam;
-                if (final) {
-                    const int o = og[i];
-                    if (a.R_out) a.R_out[o] = ri;
+                if (fl.final) {
+                    if (a.R_out) a.R_out[o] = make_float2(rx, ry);
                     if (a.V_out) a.V_out[o] = v;
                     if (a.F_out) a.F_out[o] = F;
                 } else {
                     v.x = kick(v.x, F.x, a.dt); v.y = kick(v.y, F.y, a.dt);
-                    Vh[i] = v;
-                    const float2 rn = make_float2(drift(ri.x, v.x, a.dt, a.pc.box),
-                                                  drift(ri.y, v.y, a.dt, a.pc.box));
-                    Rnext[i] = rn;
-                    const float2 rb = a.Rbuild[i];
-                    const float ddx = min_image(__fsub_rn(rn.x, rb.x), a.pc.box, a.pc.timg);
-                    const float ddy = min_image(__fsub_rn(rn.y, rb.y), a.pc.box, a.pc.timg);
+                    V[i] = v;
+                    const float xn = drift(rx, v.x, a.dt, a.pc.box), yn = drift(ry, v.y, a.dt, a.pc.box);
+                    Xn[i] = xn; Yn[i] = yn;
+                    const float2 rb = a.Rb[i];
+                    const float ddx = min_image(__fsub_rn(xn, rb.x), a.pc.box, a.pc.timg);
+                    const float ddy = min_image(__fsub_rn(yn, rb.y), a.pc.box, a.pc.timg);
                     moved |= (ddx * ddx + ddy * ddy > a.half_skin2);
                 }
             }
@@ -593,7 +638,7 @@ cells_persistent_kernel(const CellsArgs a) {
         // a particle left the skin/2 ball: ask for a rebuild before the next force evaluation.
         // The flag carries the step stamp, so it never needs clearing (no reset race).
         if (__syncthreads_or(moved) && tid == 0) __stcg(a.state + ST_FLAG, (int)(s + 2));
-        if (!final) ctx.pr ^= 1;
+        if (!fl.final) ctx.pr ^= 1;
         CL_PROF(0);
         CL_BARRIER();
         CL_PROF(1);
@@ -602,12 +647,12 @@ cells_persistent_kernel(const CellsArgs a) {
             double pe2 = 0.0, ke2 = 0.0;
             for (int k = tid; k < a.G; k += 32) {
                 pe2 += (double)__ldcg(&a.pe_part[par * a.G + k]);
-                if (want_e) ke2 += (double)__ldcg(&a.ke_part[par * a.G + k]);
+                if (fl.want_e) ke2 += (double)__ldcg(&a.ke_part[par * a.G + k]);
             }
             pe2 = warp_sum(pe2);
             ke2 = warp_sum(ke2);
             if (tid == 0) {
-                if (want_e) {
+                if (fl.want_e) {
                     float* o = rc.ke_pe + 2 * (s / rc.energy_every);
                     o[0] = (float)(0.5 * ke2);
                     o[1] = (float)(0.5 * pe2);
@@ -617,18 +662,18 @@ cells_persistent_kernel(const CellsArgs a) {
             }
         }
     }
-    if (gtid == 0) { a.state[ST_PR] = ctx.pr; a.state[ST_PV] = ctx.pv; }
+    if (gtid == 0) { a.state[ST_PR] = ctx.pr; a.state[ST_PV] = ctx.pv; a.state[ST_NTOT] = ctx.ntot; }
     if (ctx.pt && tid == 0)
         for (int k = 0; k < 11; ++k) a.prof[blockIdx.x * 12 + k] = s_pt[k];
 }
 
 // ---- stand-alone binning for ljmd_cell_assign (original order) ------------------------------------
-__global__ void cell_assign_kernel(const float2* __restrict__ R, int N, int ncell, float inv_cell,
-                                   int* __restrict__ cell_id, int* __restrict__ cell_count) {
+__global__ void cell_assign_kernel(const float2* __restrict__ R, int N, int nrows, int nbx, float inv_hy,
+                                   float inv_wx, int* __restrict__ cell_id, int* __restrict__ cell_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const float2 r = R[i];
-    const int c = cell_coord(r.y, inv_cell, ncell) * ncell + cell_coord(r.x, inv_cell, ncell);
+    const int c = strip_coord(r.y, inv_hy, nrows) * nbx + strip_coord(r.x, inv_wx, nbx);
     if (cell_id) cell_id[i] = c;
     if (cell_count) atomicAdd(&cell_count[c], 1);
 }
@@ -637,13 +682,13 @@ __global__ void cell_assign_kernel(const float2* __restrict__ R, int N, int ncel
 
 // ----------------------------------------------------------------------------------------------------
 struct Cells {
-    int G = 0, ncell = 0, ncells = 0, Npad = 0;
-    float inv_cell = 0, cell_size = 0, rlist = 0;
-    float2 *Rs[2] = {nullptr, nullptr}, *Vh[2] = {nullptr, nullptr}, *Rbuild = nullptr;
+    int G = 0, nrows = 0, nbx = 0, ncells = 0, Nalloc = 0;
+    float inv_hy = 0, inv_wx = 0, hy = 0, wx = 0, rlist = 0;
+    float *X[2] = {nullptr, nullptr}, *Y[2] = {nullptr, nullptr};
+    float2 *V[2] = {nullptr, nullptr}, *Rb = nullptr, *Fs = nullptr;
     int *orig[2] = {nullptr, nullptr};
-    int *key = nullptr, *slot_src = nullptr, *cell_count = nullptr, *cell_start = nullptr,
-        *fill = nullptr, *chunk_tot = nullptr;
-    unsigned *meta = nullptr, *nbr2 = nullptr;
+    int *key = nullptr, *rank = nullptr, *tmp = nullptr, *cell_count = nullptr, *cell_start = nullptr,
+        *row_tot = nullptr;
     float *pe_part = nullptr, *ke_part = nullptr;
     int* state = nullptr;
     unsigned* bar = nullptr;
@@ -657,50 +702,48 @@ int cells_create(ljmd_handle* h) {
     if (N > (1ll << 30)) { set_error("N too large for 32-bit particle indices"); return LJMD_E_INVALID; }
     const float rc = h->p.rc, skin = h->p.skin;
     cl->rlist = rc + skin;
-    // cells must be at least rc + skin wide, with a few ulp(box) of margin for the fp32 binning
-    const double margin = 8.0 * (double)(nextafterf(h->p.box, 2.0f * h->p.box) - h->p.box);
-    cl->ncell = (int)floor((double)h->p.box / ((double)cl->rlist + margin));
-    if (cl->ncell < 3) {
-        set_error("box %.3f is smaller than 3 cells of width rc+skin=%.3f: use the all-pairs path",
+    // rows at least rc + skin high, bins at least (rc + skin) / K wide, each with a few ulp(box) of
+    // margin for the fp32 binning (one multiply + truncation)
+    const double ulp = (double)(nextafterf(h->p.box, 2.0f * h->p.box) - h->p.box);
+    cl->nrows = (int)floor((double)h->p.box / ((double)cl->rlist + 8.0 * ulp));
+    cl->nbx   = (int)floor((double)h->p.box / ((double)cl->rlist / CL_K + 4.0 * ulp));
+    if (cl->nrows < 3 || cl->nbx < 2 * CL_K + 1) {
+        set_error("box %.3f is smaller than 3 rows of height rc+skin=%.3f: use the all-pairs path",
                   h->p.box, cl->rlist);
         return LJMD_E_INVALID;
     }
-    if (cl->ncell > 32768) cl->ncell = 32768;
-    cl->ncells = cl->ncell * cl->ncell;
-    cl->cell_size = h->p.box / (float)cl->ncell;
-    cl->inv_cell = (float)cl->ncell / h->p.box;
-    cl->Npad = (int)((N + 31) / 32 * 32);
-    // int16 index distances: one cell row (+ a 3-cell window) must stay below 32767 slots
-    if ((double)N / cl->ncell * 1.5 + 256.0 > 32767.0) {
-        set_error("cell-list: N/ncell = %.0f particles per cell row exceeds the int16 list encoding", (double)N / cl->ncell);
-        return LJMD_E_UNSUPPORTED;
-    }
+    if ((long long)cl->nrows * cl->nbx > (1ll << 30)) { set_error("cell index too large"); return LJMD_E_INVALID; }
+    cl->ncells = cl->nrows * cl->nbx;
+    cl->hy = h->p.box / (float)cl->nrows;
+    cl->wx = h->p.box / (float)cl->nbx;
+    cl->inv_hy = (float)cl->nrows / h->p.box;
+    cl->inv_wx = (float)cl->nbx / h->p.box;
+    cl->Nalloc = (int)(((N + cl->nrows + 63) / 64) * 64 + 64);
 
     int per_sm = 0;
     LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cells_persistent_kernel, CL_THREADS, 0));
     if (per_sm < 1) { set_error("cell-list kernel does not fit on an SM"); return LJMD_E_STATE; }
-    int want = 2;
-    if (const char* e = getenv("LJMD_CELLS_CTAS_PER_SM")) want = std::max(1, atoi(e));
-    per_sm = std::min(per_sm, want);
+    if (const char* e = getenv("LJMD_CELLS_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));
     long long g = (long long)per_sm * h->num_sms;
-    g = std::min<long long>(g, std::max<long long>(1, (N + CL_THREADS - 1) / CL_THREADS));
+    g = std::min<long long>(g, std::max<long long>(1, (N / 2 + CL_THREADS - 1) / CL_THREADS));
     cl->G = (int)g;
 
-    const size_t nb2 = sizeof(float2) * (size_t)cl->Npad;
+    const size_t na = (size_t)cl->Nalloc;
     for (int k = 0; k < 2; ++k) {
-        LJ_CUDA(cudaMalloc(&cl->Rs[k], nb2));
-        LJ_CUDA(cudaMalloc(&cl->Vh[k], nb2));
-        LJ_CUDA(cudaMalloc(&cl->orig[k], sizeof(int) * (size_t)cl->Npad));
+        LJ_CUDA(cudaMalloc(&cl->X[k], sizeof(float) * na));
+        LJ_CUDA(cudaMalloc(&cl->Y[k], sizeof(float) * na));
+        LJ_CUDA(cudaMalloc(&cl->V[k], sizeof(float2) * na));
+        LJ_CUDA(cudaMalloc(&cl->orig[k], sizeof(int) * na));
     }
-    LJ_CUDA(cudaMalloc(&cl->Rbuild, 2 * nb2));      // second half: force scratch for the thermostat
-    LJ_CUDA(cudaMalloc(&cl->key, sizeof(int) * (size_t)cl->Npad));
-    LJ_CUDA(cudaMalloc(&cl->slot_src, sizeof(int) * (size_t)cl->Npad));
-    LJ_CUDA(cudaMalloc(&cl->meta, sizeof(unsigned) * (size_t)cl->Npad));
-    LJ_CUDA(cudaMalloc(&cl->nbr2, sizeof(unsigned) * (size_t)cl->Npad * (CL_MAXN / 2)));
+    LJ_CUDA(cudaMalloc(&cl->Rb, sizeof(float2) * na));
+    LJ_CUDA(cudaMalloc(&cl->Fs, sizeof(float2) * na));
+    LJ_CUDA(cudaMalloc(&cl->key, sizeof(int) * na));
+    LJ_CUDA(cudaMalloc(&cl->rank, sizeof(int) * na));
+    LJ_CUDA(cudaMalloc(&cl->tmp, sizeof(int) * na));
     LJ_CUDA(cudaMalloc(&cl->cell_count, sizeof(int) * (size_t)cl->ncells));
-    LJ_CUDA(cudaMalloc(&cl->fill, sizeof(int) * (size_t)cl->ncells));
+    LJ_CUDA(cudaMemset(cl->cell_count, 0, sizeof(int) * (size_t)cl->ncells));
     LJ_CUDA(cudaMalloc(&cl->cell_start, sizeof(int) * ((size_t)cl->ncells + 1)));
-    LJ_CUDA(cudaMalloc(&cl->chunk_tot, sizeof(int) * cl->G));
+    LJ_CUDA(cudaMalloc(&cl->row_tot, sizeof(int) * (size_t)cl->nrows));
     LJ_CUDA(cudaMalloc(&cl->pe_part, sizeof(float) * 2 * cl->G));
     LJ_CUDA(cudaMalloc(&cl->ke_part, sizeof(float) * 2 * cl->G));
     LJ_CUDA(cudaMalloc(&cl->state, sizeof(int) * ST_WORDS));
@@ -713,10 +756,10 @@ int cells_create(ljmd_handle* h) {
 void cells_destroy(ljmd_handle* h) {
     Cells* cl = h->cells;
     if (!cl) return;
-    for (int k = 0; k < 2; ++k) { cudaFree(cl->Rs[k]); cudaFree(cl->Vh[k]); cudaFree(cl->orig[k]); }
-    cudaFree(cl->Rbuild); cudaFree(cl->key); cudaFree(cl->slot_src); cudaFree(cl->meta);
-    cudaFree(cl->nbr2); cudaFree(cl->cell_count); cudaFree(cl->fill);
-    cudaFree(cl->cell_start); cudaFree(cl->chunk_tot); cudaFree(cl->pe_part); cudaFree(cl->ke_part);
+    for (int k = 0; k < 2; ++k) { cudaFree(cl->X[k]); cudaFree(cl->Y[k]); cudaFree(cl->V[k]); cudaFree(cl->orig[k]); }
+    cudaFree(cl->Rb); cudaFree(cl->Fs); cudaFree(cl->key); cudaFree(cl->rank); cudaFree(cl->tmp);
+    cudaFree(cl->cell_count); cudaFree(cl->cell_start); cudaFree(cl->row_tot);
+    cudaFree(cl->pe_part); cudaFree(cl->ke_part);
     cudaFree(cl->state); cudaFree(cl->bar); cudaFree(cl->prof);
     delete cl;
     h->cells = nullptr;
@@ -725,17 +768,15 @@ void cells_destroy(ljmd_handle* h) {
 static void fill_args(ljmd_handle* h, CellsArgs& a) {
     Cells* cl = h->cells;
     a.pc = h->pc;
-    a.N = (int)h->p.N; a.Npad = cl->Npad; a.G = cl->G;
-    a.ncell = cl->ncell; a.ncells = cl->ncells;
-    a.inv_cell = cl->inv_cell; a.cell_size = cl->cell_size;
-    a.rlist2 = cl->rlist * cl->rlist;
+    a.N = (int)h->p.N; a.Nalloc = cl->Nalloc; a.G = cl->G;
+    a.nrows = cl->nrows; a.nbx = cl->nbx; a.ncells = cl->ncells;
+    a.inv_hy = cl->inv_hy; a.inv_wx = cl->inv_wx;
     a.half_skin2 = (0.5f * h->p.skin) * (0.5f * h->p.skin);
     a.dt = h->p.dt;
-    for (int k = 0; k < 2; ++k) { a.Rs[k] = cl->Rs[k]; a.Vh[k] = cl->Vh[k]; a.orig[k] = cl->orig[k]; }
-    a.Rbuild = cl->Rbuild;
-    a.key = cl->key; a.slot_src = cl->slot_src; a.cell_count = cl->cell_count;
-    a.cell_start = cl->cell_start; a.fill = cl->fill; a.chunk_tot = cl->chunk_tot;
-    a.meta = cl->meta; a.nbr2 = cl->nbr2;
+    for (int k = 0; k < 2; ++k) { a.X[k] = cl->X[k]; a.Y[k] = cl->Y[k]; a.V[k] = cl->V[k]; a.orig[k] = cl->orig[k]; }
+    a.Rb = cl->Rb; a.Fs = cl->Fs;
+    a.key = cl->key; a.rank = cl->rank; a.tmp = cl->tmp;
+    a.cell_count = cl->cell_count; a.cell_start = cl->cell_start; a.row_tot = cl->row_tot;
     a.pe_part = cl->pe_part; a.ke_part = cl->ke_part;
     a.state = cl->state; a.bar = cl->bar; a.prof = cl->prof;
 }
@@ -759,7 +800,7 @@ int cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_
         LJ_CUDA(cudaMemsetAsync(rc.traj, 0, sizeof(float2) * N * rc.S, st));      // MD:89
     // fresh call: parities 0, rebuild counter 0, flag 0 (the error word is sticky)
     LJ_CUDA(cudaMemsetAsync(cl->state, 0, sizeof(int) * 3, st));
-    LJ_CUDA(cudaMemsetAsync(cl->state + ST_FLAG, 0, sizeof(int), st));
+    LJ_CUDA(cudaMemsetAsync(cl->state + ST_FLAG, 0, sizeof(int) * 2, st));
     CellsArgs a{};
     fill_args(h, a);
     a.R_in = R_in; a.V_in = V_in;
@@ -784,9 +825,9 @@ int cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_
         LJ_CUDA(cudaStreamSynchronize(st));
         std::vector<long long> pv(12 * cl->G);
         LJ_CUDA(cudaMemcpy(pv.data(), cl->prof, sizeof(long long) * pv.size(), cudaMemcpyDeviceToHost));
-        const char* nm[10] = {"force+integrate", "step barrier", "R1 clear", "R2 bin+hist", "R3 scan pass1",
-                              "R4 scan pass2", "R5 scatter", "R6a cell sort", "R6b gather", "R7 list build"};
-        for (int k = 0; k < 10; ++k) {
+        const char* nm[7] = {"force+integrate", "step barrier", "B1 bin+hist", "B2 row totals",
+                             "B3 scan", "B4 scatter", "B5 order+gather"};
+        for (int k = 0; k < 7; ++k) {
             double mean = 0, mx = 0;
             for (int c = 0; c < cl->G; ++c) { mean += pv[c * 12 + k]; mx = std::max<double>(mx, (double)pv[c * 12 + k]); }
             fprintf(stderr, "[ljmd cells prof] %-16s mean %12.0f  max %12.0f clocks (launch total)\n", nm[k], mean / cl->G, mx);
@@ -795,11 +836,13 @@ int cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_
     return 0;
 }
 
-int cells_geometry(ljmd_handle* h, int* ncell, float* cell, float* inv_cell) {
+int cells_geometry(ljmd_handle* h, int* nrows, int* nbx, int* kbins, float* inv_hy, float* inv_wx) {
     Cells* cl = h->cells;
-    if (ncell) *ncell = cl->ncell;
-    if (cell) *cell = cl->cell_size;
-    if (inv_cell) *inv_cell = cl->inv_cell;
+    if (nrows) *nrows = cl->nrows;
+    if (nbx) *nbx = cl->nbx;
+    if (kbins) *kbins = CL_K;
+    if (inv_hy) *inv_hy = cl->inv_hy;
+    if (inv_wx) *inv_wx = cl->inv_wx;
     return 0;
 }
 
@@ -807,7 +850,8 @@ int cells_assign(ljmd_handle* h, const float2* R, int* cell_id, int* cell_count)
     Cells* cl = h->cells;
     const int N = (int)h->p.N;
     if (cell_count) LJ_CUDA(cudaMemsetAsync(cell_count, 0, sizeof(int) * (size_t)cl->ncells, h->stream));
-    cell_assign_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(R, N, cl->ncell, cl->inv_cell, cell_id, cell_count);
+    cell_assign_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(R, N, cl->nrows, cl->nbx, cl->inv_hy,
+                                                               cl->inv_wx, cell_id, cell_count);
     LJ_CUDA(cudaGetLastError());
     h->launches++;
     return 0;
@@ -815,11 +859,12 @@ int cells_assign(ljmd_handle* h, const float2* R, int* cell_id, int* cell_count)
 
 int cells_neighbor_count(ljmd_handle* h, const float2* R, float radius, int* nbr_count) {
     Cells* cl = h->cells;
-    if (!(radius > 0.0f) || radius > cl->cell_size) {
-        set_error("neighbor_count radius %.4f must be in (0, cell size %.4f]", radius, cl->cell_size);
+    if (!(radius > 0.0f) || radius > cl->rlist) {
+        set_error("neighbor_count radius %.4f must be in (0, rc + skin = %.4f]", radius, cl->rlist);
         return LJMD_E_INVALID;
     }
     LJ_CUDA(cudaMemsetAsync(cl->state, 0, sizeof(int) * 3, h->stream));
+    LJ_CUDA(cudaMemsetAsync(cl->state + ST_FLAG, 0, sizeof(int) * 2, h->stream));
     CellsArgs a{};
     fill_args(h, a);
     a.R_in = R; a.V_in = nullptr;
@@ -843,10 +888,6 @@ int cells_check_error(ljmd_handle* h) {
     if (!cl) return 0;
     int e = 0;
     LJ_CUDA(cudaMemcpy(&e, cl->state + ST_ERR, sizeof(int), cudaMemcpyDeviceToHost));
-    if (e & CERR_LIST_OVERFLOW) {
-        set_error("cell-list: a particle has more than %d neighbours within rc+skin", CL_MAXN);
-        return LJMD_E_STATE;
-    }
     if (e) { set_error("cell-list persistent kernel: grid barrier timed out (flag %d)", e); return LJMD_E_STATE; }
     return 0;
 }

@@ -169,8 +169,11 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target,
     if (threadIdx.x == 0) {
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         long long t0 = clock64();
-        while (ld_acquire_gpu(counter) < target) {
-            if (clock64() - t0 > (1ll << 32)) { atomicExch(err, 1); break; }
+        // once a barrier has timed out the run is void: later barriers fall through at once
+        if (__ldcg(err) == 0) {
+            while (ld_acquire_gpu(counter) < target) {
+                if (clock64() - t0 > (1ll << 32)) { atomicExch(err, 1); break; }
+            }
         }
     }
     __syncthreads();                       // ... and the acquire is ordered before every thread's reads

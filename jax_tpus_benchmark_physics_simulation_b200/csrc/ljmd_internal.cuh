@@ -96,7 +96,7 @@ int  cells_create(ljmd_handle* h);
 void cells_destroy(ljmd_handle* h);
 int  cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_out,
                float2* V_out, float2* F_out, float* pe_out, const RunCtl& rc);
-int  cells_geometry(ljmd_handle* h, int* ncell, float* cell, float* inv_cell);
+int  cells_geometry(ljmd_handle* h, int* nrows, int* nbx, int* kbins, float* inv_hy, float* inv_wx);
 int  cells_assign(ljmd_handle* h, const float2* R, int* cell_id, int* cell_count);
 int  cells_neighbor_count(ljmd_handle* h, const float2* R, float radius, int* nbr_count);
 long long cells_last_rebuilds(ljmd_handle* h);

@@ -270,16 +270,19 @@ class LJSimulation:
 
     # ------------------------------------------------------------------ cell-list introspection
     def cell_geometry(self):
-        nc, cs, ic = ctypes.c_int32(), ctypes.c_float(), ctypes.c_float()
-        _lib.check(self.lib.ljmd_cell_geometry(self._h, ctypes.byref(nc), ctypes.byref(cs),
-                                               ctypes.byref(ic)), "ljmd_cell_geometry")
-        return nc.value, np.float32(cs.value), np.float32(ic.value)
+        """(nrows, nbins_x, kbins, inv_row_height, inv_bin_width) of the strip-cell grid."""
+        nr, nb, kb = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        ih, iw = ctypes.c_float(), ctypes.c_float()
+        _lib.check(self.lib.ljmd_cell_geometry(self._h, ctypes.byref(nr), ctypes.byref(nb),
+                                               ctypes.byref(kb), ctypes.byref(ih), ctypes.byref(iw)),
+                   "ljmd_cell_geometry")
+        return nr.value, nb.value, kb.value, np.float32(ih.value), np.float32(iw.value)
 
     def cell_assign(self, R):
         R = self._dev(R, (self.N, 2))
-        nc, _, _ = self.cell_geometry()
+        nr, nb, _, _, _ = self.cell_geometry()
         cid = torch.empty(self.N, dtype=torch.int32, device=self.device)
-        cnt = torch.empty(nc * nc, dtype=torch.int32, device=self.device)
+        cnt = torch.empty(nr * nb, dtype=torch.int32, device=self.device)
         self._check_stream()
         _lib.check(self.lib.ljmd_cell_assign(self._h, R.data_ptr(), cid.data_ptr(), cnt.data_ptr()),
                    "ljmd_cell_assign")

@@ -151,19 +151,20 @@ void orc_run(int64_t N, float* R, float* V, float box, float sigma, float eps, f
 }
 
 /* ---- cell-list recount (new functionality) -------------------------
- * cell index: c = min((int)(x * inv_cell), ncell-1), one fp32 multiply then truncation
- * (x >= 0 so truncation == floor); the min handles x == box (MD:72 closed interval).   */
-void orc_cell_assign(int64_t N, const float* R, int32_t ncell, float inv_cell,
-                     int32_t* cell_id, int32_t* cell_count) {
-    if (cell_count) memset(cell_count, 0, sizeof(int32_t) * (size_t)ncell * ncell);
+ * strip cells: row = min((int)(y * inv_hy), nrows-1), bin = min((int)(x * inv_wx), nbx-1),
+ * cell = row * nbx + bin; one fp32 multiply then truncation (coordinates >= 0 so truncation
+ * == floor); the min handles a coordinate == box (MD:72 closed interval).                */
+void orc_cell_assign(int64_t N, const float* R, int32_t nrows, int32_t nbx, float inv_hy,
+                     float inv_wx, int32_t* cell_id, int32_t* cell_count) {
+    if (cell_count) memset(cell_count, 0, sizeof(int32_t) * (size_t)nrows * nbx);
     for (int64_t i = 0; i < N; ++i) {
-        int32_t cx = (int32_t)(R[2 * i] * inv_cell);
-        int32_t cy = (int32_t)(R[2 * i + 1] * inv_cell);
-        if (cx > ncell - 1) cx = ncell - 1;
-        if (cy > ncell - 1) cy = ncell - 1;
+        int32_t cx = (int32_t)(R[2 * i] * inv_wx);
+        int32_t cy = (int32_t)(R[2 * i + 1] * inv_hy);
+        if (cx > nbx - 1) cx = nbx - 1;
+        if (cy > nrows - 1) cy = nrows - 1;
         if (cx < 0) cx = 0;
         if (cy < 0) cy = 0;
-        int32_t c = cy * ncell + cx;
+        int32_t c = cy * nbx + cx;
         if (cell_id) cell_id[i] = c;
         if (cell_count) cell_count[c]++;
     }

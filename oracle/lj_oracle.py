@@ -235,8 +235,8 @@ def c_lib():
                                 ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int64,
                                 ctypes.c_int64, f32p, ctypes.c_int64, f64p, ctypes.c_float,
                                 ctypes.c_int64, ctypes.c_int]
-        lib.orc_cell_assign.argtypes = [ctypes.c_int64, f32p, ctypes.c_int32, ctypes.c_float,
-                                        i32p, i32p]
+        lib.orc_cell_assign.argtypes = [ctypes.c_int64, f32p, ctypes.c_int32, ctypes.c_int32,
+                                        ctypes.c_float, ctypes.c_float, i32p, i32p]
         lib.orc_neighbor_count.argtypes = [ctypes.c_int64, f32p, ctypes.c_float, ctypes.c_float,
                                            i32p]
         lib.orc_forces_cells.argtypes = [ctypes.c_int64, f32p, ctypes.c_float, ctypes.c_float,
@@ -300,14 +300,15 @@ def c_run(R, V, box, dt, nsteps, sample_every=0, rc=None, energy_every=0, thermo
     return R, V, traj, ke_pe
 
 
-def c_cell_assign(R, ncell, inv_cell):
+def c_cell_assign(R, nrows, nbx, inv_hy, inv_wx):
+    """Strip-cell recount: cell = row * nbx + bin (see orc_cell_assign)."""
     R, Rp = _f32(R)
     N = R.shape[0]
     cid = np.empty(N, dtype=np.int32)
-    cnt = np.empty(ncell * ncell, dtype=np.int32)
+    cnt = np.empty(nrows * nbx, dtype=np.int32)
     i32p = ctypes.POINTER(ctypes.c_int32)
-    c_lib().orc_cell_assign(N, Rp, ncell, float(inv_cell), cid.ctypes.data_as(i32p),
-                            cnt.ctypes.data_as(i32p))
+    c_lib().orc_cell_assign(N, Rp, nrows, nbx, float(inv_hy), float(inv_wx),
+                            cid.ctypes.data_as(i32p), cnt.ctypes.data_as(i32p))
     return cid, cnt
 
 

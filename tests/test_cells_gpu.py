@@ -32,11 +32,12 @@ def test_cell_assignment_bit_exact(oracle, N):
     R[0] = (0.0, box)                      # closed-interval edges (MD:72): x == 0, y == box
     R[1] = (box, np.float32(0.0))
     sim = _sim(N)
-    ncell, cell, inv_cell = sim.cell_geometry()
-    assert ncell == int(np.floor(float(box) / 2.8)) and ncell >= 3
-    assert float(cell) >= 2.8
+    nrows, nbx, kb, inv_hy, inv_wx = sim.cell_geometry()
+    assert nrows == int(np.floor(float(box) / 2.8)) and nrows >= 3
+    assert kb == 4 and nbx >= 2 * kb + 1
+    assert 1.0 / float(inv_hy) >= 2.8 and kb / float(inv_wx) >= 2.8       # rows / K bins cover rc + skin
     cid, cnt = sim.cell_assign(R)
-    cid_c, cnt_c = oracle.c_cell_assign(R, ncell, inv_cell)
+    cid_c, cnt_c = oracle.c_cell_assign(R, nrows, nbx, inv_hy, inv_wx)
     assert np.array_equal(cid.cpu().numpy(), cid_c)
     assert np.array_equal(cnt.cpu().numpy(), cnt_c)
     assert int(cnt.sum()) == N
@@ -95,7 +96,7 @@ def test_one_step_energy_vs_oracle(oracle):
 
 
 def test_trajectory_with_rebuilds_vs_oracle(oracle):
-    """N = 400 fits 7x7 cells: 200 steps at dt = 0.005 cross several rebuilds."""
+    """N = 400 fits 7 rows x 31 bins: 200 steps at dt = 0.005 cross several rebuilds."""
     N, dt = 400, 0.005
     R, V, box = lattice_jitter(N, seed=0)
     sim = _sim(N, dt=dt)
@@ -164,10 +165,10 @@ def test_full_size_config4_properties(oracle):
     N, dt = 4194304, 0.005
     R, V, box = lattice_jitter(N, seed=0)
     sim = _sim(N, dt=dt)
-    ncell, cell, inv_cell = sim.cell_geometry()
-    assert ncell == 817
+    nrows, nbx, kb, inv_hy, inv_wx = sim.cell_geometry()
+    assert nrows == 817 and nbx == int(np.floor(float(box) / (0.7 + 4.0 * float(np.spacing(np.float32(box))))))
     cid, cnt = sim.cell_assign(R)
-    cid_c, cnt_c = oracle.c_cell_assign(R, ncell, inv_cell)
+    cid_c, cnt_c = oracle.c_cell_assign(R, nrows, nbx, inv_hy, inv_wx)
     assert np.array_equal(cid.cpu().numpy(), cid_c) and np.array_equal(cnt.cpu().numpy(), cnt_c)
     got = sim.neighbor_count(R, 2.8).cpu().numpy()
     assert np.array_equal(got, oracle.c_neighbor_count(R, box, 2.8))
