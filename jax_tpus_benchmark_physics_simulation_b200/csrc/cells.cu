@@ -23,12 +23,19 @@
 //                        gives the slot's cell, hence its three candidate ranges)
 //   cell_start  int32   prefix-sum cell index over nrows*nbx cells (+1)
 //
-// One PERSISTENT cooperative kernel runs a whole ljmd_run().  Per step ONE pass over the state
-// (each thread owns two adjacent slots: forces from the three ranges + velocity-Verlet + energies +
-// displacement test; state read once, written once) and one grid barrier.  The rebuild (bin +
-// histogram with rank capture -> row-structured prefix sum -> scatter -> deterministic in-cell
-// order by original index + gather) runs inside the same kernel under a grid-uniform condition:
-// no host round trip (MD:82,103).
+// One PERSISTENT cooperative kernel runs a whole ljmd_run().  Per step ONE pass over the state and
+// one grid barrier.  A row is cut into chunks of 512 slots; a CTA is 8 consumer warps + 1 producer
+// warp.  The producer runs one chunk ahead: it looks up the chunk's three row windows and issues
+// TMA bulk copies (cp.async.bulk, mbarrier complete_tx) of everything the chunk needs — the x / y
+// windows of rows r-1, r, r+1, the matching slices of the cell index, and the chunk's own Rb / V /
+// orig — into a 2-stage shared-memory ring; the consumers (each thread owns two adjacent slots)
+// evaluate forces from shared memory only, then velocity-Verlet + energies + displacement test and
+// write the new state: each particle's state is read once and written once per step and no load
+// in the pair loop can miss.  Chunks are handed out dynamically (one atomic per chunk); energies
+// are per-chunk partials reduced in chunk order, so results do not depend on the schedule.
+// The rebuild (bin + histogram with rank capture -> row-structured prefix sum -> scatter ->
+// deterministic in-cell order by original index + gather) runs inside the same kernel under a
+// grid-uniform condition: no host round trip (MD:82,103).
 #include "ljmd_device.cuh"
 
 #include <algorithm>
@@ -38,11 +45,14 @@ namespace ljmd {
 
 namespace {
 
-constexpr int   CL_THREADS = 256;
-#ifndef LJMD_CELLS_MINBLOCKS
-#define LJMD_CELLS_MINBLOCKS 2
-#endif
-constexpr int   CL_MINBLOCKS = LJMD_CELLS_MINBLOCKS;
+constexpr int   CL_CONSUMERS = 256;               // consumer threads: one slot pair each
+constexpr int   CL_THREADS   = CL_CONSUMERS + 32;  // + one producer warp
+constexpr int   CL_CH        = 2 * CL_CONSUMERS;   // slots per chunk
+constexpr int   CL_NST       = 2;                  // stages of the shared-memory ring
+constexpr int   CL_WMAX      = 896;                // staged window capacity per row (slots): a lattice
+                                                   // row of 3 lattice lines beside one of 2 needs 1.5 * CL_CH
+constexpr int   CL_CSMAX     = 512;                // staged cell-index slice capacity per row
+// (2 CTAs x 9 warps per SM: one sub-partition hosts 5 warps, which caps the kernel at 96 registers)
 constexpr int   CL_K       = 4;        // bins per (rc + skin)
 constexpr int   CL_ORDER_MAX = 64;     // cells denser than this keep arrival order (see B5)
 // Pad slots sit far outside any box, each at its OWN place (pad_x): two pads must never coincide,
@@ -54,7 +64,26 @@ constexpr float CL_SENT    = 1.0e8f;
 #define LJMD_CELLS_RCP_PRODUCT 1       // one MUFU.RCP per TWO pairs (1/(a*b) trick), see eval_set
 #endif
 
-enum { ST_PR = 0, ST_PV = 1, ST_REBUILDS = 2, ST_ERR = 3, ST_FLAG = 4, ST_NTOT = 5, ST_WORDS = 8 };
+enum { ST_PR = 0, ST_PV = 1, ST_REBUILDS = 2, ST_ERR = 3, ST_FLAG = 4, ST_NTOT = 5, ST_NCHUNKS = 6,
+       ST_WORDS = 8 };
+
+// one stage of the ring: everything a chunk's consumers read (all 16-byte aligned for the bulk copies)
+struct __align__(16) Stage {
+    float  x[3][CL_WMAX];          // x window of rows r-1, r, r+1
+    float  y[3][CL_WMAX];
+    float2 rb[CL_CH + 4];          // own build positions, velocities, original indices
+    float2 v[CL_CH + 4];
+    int    og[CL_CH + 4];
+    int    cs[3][CL_CSMAX];        // cell_start slices of the three rows
+};
+struct StageMeta {
+    int chunk;                     // chunk id, -1 = end of step
+    int row, slot0, n;             // row, first slot, number of slots (even)
+    int direct;                    // 1 = windows too large for the stage: consumers read global memory
+    int ws[3];                     // first staged slot of each window   (multiple of 4)
+    int cb[3];                     // first staged cell of each cs slice (multiple of 4)
+    int own0;                      // first staged slot of rb / v / og   (multiple of 4)
+};
 enum { CERR_BARRIER = 1 };
 
 struct CellsArgs {
@@ -69,7 +98,10 @@ struct CellsArgs {
     float2* Rb;
     float2* Fs;                     // forces held across the thermostat barrier
     int *key, *rank, *tmp, *cell_count, *cell_start, *row_tot;
-    float  *pe_part, *ke_part;      // [2*G]
+    int2*   chunk_tab;              // (row, first slot) of every chunk
+    int*    sched;                  // [2] dynamic chunk counters (by step parity)
+    int     maxchunks;
+    float  *pe_part, *ke_part;      // [2*maxchunks] per-chunk partials (by step parity)
     int*      state;                // ST_* words
     unsigned* bar;
     const float2* R_in;
@@ -124,7 +156,8 @@ __device__ __forceinline__ int block_exscan(int v, int* swarp /* CL_THREADS/32 +
 
 struct Ctx {
     unsigned epoch;
-    int pr, pv, ntot;
+    unsigned it;        // ring iteration counter (same in producer and consumers)
+    int pr, pv, ntot, nchunks;
     long long* pt;      // shared-memory phase clocks (thread 0), or nullptr
 };
 
@@ -177,12 +210,23 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan) {
         float* Yn = a.Y[ctx.pr ^ 1];
         int* on = a.orig[ctx.pv ^ 1];
         for (int r = blockIdx.x; r < a.nrows; r += a.G) {
-            int s = 0;
-            for (int q = tid; q < r; q += CL_THREADS) s += (a.row_tot[q] + 1) & ~1;
-            int carry;
+            int s = 0, sc = 0;
+            for (int q = tid; q < r; q += CL_THREADS) {
+                const int len = (a.row_tot[q] + 1) & ~1;
+                s += len;
+                sc += (len + CL_CH - 1) / CL_CH;
+            }
+            int carry, chunk0;
             (void)block_exscan(s, sscan, &carry);
+            (void)block_exscan(sc, sscan, &chunk0);
             const int rtot = a.row_tot[r];
             const int row0 = carry;
+            // the row's chunks: consecutive runs of CL_CH slots, never straddling a row
+            {
+                const int len = (rtot + 1) & ~1, nch = (len + CL_CH - 1) / CL_CH;
+                for (int j = tid; j < nch; j += CL_THREADS) a.chunk_tab[chunk0 + j] = make_int2(r, row0 + j * CL_CH);
+                if (r == a.nrows - 1 && tid == 0) a.state[ST_NCHUNKS] = chunk0 + nch;
+            }
             for (int bb = 0; bb < a.nbx; bb += CL_THREADS) {
                 const int b = bb + tid;
                 int v = 0;
@@ -251,6 +295,7 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan) {
             on[d] = orig_old[ksel];
         }
         ctx.ntot = ntot_new;
+        ctx.nchunks = __ldcg(a.state + ST_NCHUNKS);
     }
     ctx.pr ^= 1;
     ctx.pv ^= 1;
@@ -270,41 +315,35 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan) {
 //   {r2 < rc2} is the oracle's.
 //   LJMD_CELLS_RCP_PRODUCT: 1/r2 of the two pairs of a set from ONE MUFU.RCP of the product
 //   (ir2_a = r2_b * rcp(r2_a * r2_b)): MUFU issues at 1/8 rate and would otherwise co-limit the loop.
-// MODE 0: interior ranges of the rows above/below: no self pair possible, cutoff mask is a 1.0/0.0
-//         multiply (FSET + FMUL2).
-// MODE 1: interior range of the particle's own row: the straight set at m == p is the self pair,
-//         masked by select (which also discards the NaN of 0 * inf).
-// MODE 2: edge warps: exact minimum image on every displacement and per-pair keep predicates
-//         (exact range bounds, general self test).
-template <bool PE, int MODE>
+// KEEP:   per-pair keep predicates are applied (self pair of the own row; exact bounds of edge ranges).
+// MINIMG: exact minimum image on every displacement (edge warps).
+// The cutoff is a select on the ALU pipe (FSETP + SEL): the FMA pipe is the one that saturates (a
+// packed FP32x2 instruction occupies it for two cycles), so nothing that can run elsewhere is put on
+// it; the select also discards the NaN of a masked 0 * inf.
+template <bool PE, bool MINIMG, bool KEEP>
 __device__ __forceinline__ void eval_set(const PairConsts& pc, const PairConsts2& c2, float2 nxi,
                                          float2 nyi, float2 xj, float2 yj, bool keepx, bool keepy,
                                          float2& ax, float2& ay, float2& pe2) {
     float2 dx = __fadd2_rn(xj, nxi);
     float2 dy = __fadd2_rn(yj, nyi);
-    if (MODE == 2) {
+    if (MINIMG) {
         dx.x = min_image(dx.x, pc.box, pc.timg); dx.y = min_image(dx.y, pc.box, pc.timg);
         dy.x = min_image(dy.x, pc.box, pc.timg); dy.y = min_image(dy.y, pc.box, pc.timg);
     }
     const float2 r2 = __ffma2_rn(__fmul2_rn(dx, dx), c2.one, __fmul2_rn(dy, dy));
     float2 ir2;
-    if (MODE == 0) {
-        const float2 msk = make_float2((r2.x < pc.rc2) ? 1.0f : 0.0f, (r2.y < pc.rc2) ? 1.0f : 0.0f);
 #if LJMD_CELLS_RCP_PRODUCT
-        const float rp = rcp_approx(__fmul_rn(r2.x, r2.y));
-        ir2 = __fmul2_rn(__fmul2_rn(make_float2(r2.y, r2.x), msk), make_float2(rp, rp));
+    const float rp = rcp_approx(__fmul_rn(r2.x, r2.y));
+    ir2 = __fmul2_rn(make_float2(r2.y, r2.x), make_float2(rp, rp));
 #else
-        ir2 = __fmul2_rn(make_float2(rcp_approx(r2.x), rcp_approx(r2.y)), msk);
+    ir2 = make_float2(rcp_approx(r2.x), rcp_approx(r2.y));
 #endif
-    } else {
-#if LJMD_CELLS_RCP_PRODUCT
-        const float rp = rcp_approx(__fmul_rn(r2.x, r2.y));
-        ir2 = make_float2(__fmul_rn(r2.y, rp), __fmul_rn(r2.x, rp));
-#else
-        ir2 = make_float2(rcp_approx(r2.x), rcp_approx(r2.y));
-#endif
+    if (KEEP) {
         ir2.x = (keepx & (r2.x < pc.rc2)) ? ir2.x : 0.0f;
         ir2.y = (keepy & (r2.y < pc.rc2)) ? ir2.y : 0.0f;
+    } else {
+        ir2.x = (r2.x < pc.rc2) ? ir2.x : 0.0f;
+        ir2.y = (r2.y < pc.rc2) ? ir2.y : 0.0f;
     }
     const float2 ir6 = __fmul2_rn(__fmul2_rn(ir2, ir2), ir2);
     const float2 f = __fmul2_rn(__ffma2_rn(ir6, c2.c12, c2.nc6), __fmul2_rn(ir6, ir2));
@@ -322,32 +361,35 @@ __device__ __forceinline__ void prefetch_l1(const void* p) {
 }
 
 // interior: slots [2*m0, 2*m1) (range aligned outwards to slot pairs: the extra slots belong to the
-// same row and to bins outside the stencil, hence beyond rc, and to no other range of this thread)
-template <bool PE, bool SELF>
+// same row and to bins outside the stencil, hence beyond rc, and to no other range of this thread).
+// pself = the thread's own slot pair if this is its own row, else -1.  ONE instance of this loop
+// serves all three rows (it is the hot code: it has to stay inside the instruction cache).
+template <bool PE>
 __device__ __forceinline__ void row_range(const PairConsts& pc, const PairConsts2& c2,
                                           const float2* __restrict__ X2, const float2* __restrict__ Y2,
-                                          int m0, int m1, int p, float2 nxi, float2 nyi, float2 nxs,
+                                          int m0, int m1, int pself, float2 nxi, float2 nyi, float2 nxs,
                                           float2 nys, PairAcc& acc) {
 #pragma unroll 2
     for (int m = m0; m < m1; ++m) {
         const float2 xj = X2[m], yj = Y2[m];
-        const bool k = (m != p);
-        eval_set<PE, SELF ? 1 : 0>(pc, c2, nxi, nyi, xj, yj, k, k, acc.axA, acc.ayA, acc.peA);
-        eval_set<PE, 0>(pc, c2, nxs, nys, xj, yj, true, true, acc.axB, acc.ayB, acc.peB);
+        const bool k = (m != pself);
+        eval_set<PE, false, true >(pc, c2, nxi, nyi, xj, yj, k, k, acc.axA, acc.ayA, acc.peA);
+        eval_set<PE, false, false>(pc, c2, nxs, nys, xj, yj, true, true, acc.axB, acc.ayB, acc.peB);
     }
 }
 
 // edge: slots [s, e) exactly, minimum image, any candidate may be one of the thread's own slots
+// (rare path: kept out of line, generic pointers — the window may be shared or global memory)
 template <bool PE>
-__device__ __forceinline__ void edge_range(const PairConsts& pc, const PairConsts2& c2,
-                                           const float2* __restrict__ X2, const float2* __restrict__ Y2,
-                                           int s, int e, int p, float2 nxi, float2 nyi, float2 nxs,
-                                           float2 nys, PairAcc& acc) {
+__device__ __noinline__ void edge_range(const PairConsts& pc, const PairConsts2& c2,
+                                        const float2* X2, const float2* Y2,
+                                        int s, int e, int p, float2 nxi, float2 nyi, float2 nxs,
+                                        float2 nys, PairAcc& acc) {
     for (int m = s >> 1; m < ((e + 1) >> 1); ++m) {
         const float2 xj = X2[m], yj = Y2[m];
         const bool v0 = (2 * m >= s), v1 = (2 * m + 1 < e), own = (m == p);
-        eval_set<PE, 2>(pc, c2, nxi, nyi, xj, yj, v0 & !own, v1 & !own, acc.axA, acc.ayA, acc.peA);
-        eval_set<PE, 2>(pc, c2, nxs, nys, xj, yj, v0, v1, acc.axB, acc.ayB, acc.peB);
+        eval_set<PE, true, true>(pc, c2, nxi, nyi, xj, yj, v0 & !own, v1 & !own, acc.axA, acc.ayA, acc.peA);
+        eval_set<PE, true, true>(pc, c2, nxs, nys, xj, yj, v0, v1, acc.axB, acc.ayB, acc.peB);
     }
 }
 
@@ -420,120 +462,308 @@ __device__ __forceinline__ bool finish_particle(const CellsArgs& a, const StepFl
     return ddx * ddx + ddy * ddy > a.half_skin2;
 }
 
-template <bool PE>
-__device__ __forceinline__ void force_pass(const CellsArgs& a, const Ctx& ctx, const StepFlags& fl,
-                                           float& pe_thread, float& ke_thread, int& moved) {
-    const int tid = threadIdx.x, gsz = a.G * CL_THREADS;
-    const PairConsts pc = a.pc;
-    const PairConsts2 c2 = make_pair_consts2(pc);
+// ---- mbarrier / TMA bulk-copy primitives (sm_90+ PTX; SASS: SYNCS.*, UBLKCP) ------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (bytes and both addresses multiples of 16), completion on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// order generic-proxy accesses (the previous step's st.global, made visible by the grid barrier)
+// against the async proxy (the bulk copies that read them)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CL_CONSUMERS) : "memory"); }
+
+// sum over the consumer threads (fixed shuffle tree + fixed warp order); result valid in thread 0
+__device__ __forceinline__ float consumer_sum(float v, float* sred /* CL_CONSUMERS/32 */) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    consumer_sync();
+    if (l == 0) sred[w] = v;
+    consumer_sync();
+    float t = 0.0f;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < CL_CONSUMERS / 32; ++k) t += sred[k];
+    }
+    return t;
+}
+
+// sum of n floats in fixed order by the whole CTA, in double; result valid in every thread
+__device__ __forceinline__ double block_sum_array(const float* p, int n, double* sdbl /* CL_THREADS/32 */) {
+    double t = 0.0;
+    for (int k = threadIdx.x; k < n; k += CL_THREADS) t += (double)__ldcg(p + k);
+    t = warp_sum(t);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sdbl[threadIdx.x >> 5] = t;
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < CL_THREADS / 32; ++k) tot += sdbl[k];
+    return tot;
+}
+
+// ---- producer: one chunk ahead of the consumers -----------------------------------------------------
+__device__ __forceinline__ void produce_step(const CellsArgs& a, Ctx& ctx, Stage* stages, StageMeta* meta,
+                                             unsigned long long* full, unsigned long long* empty, int par) {
     const float* __restrict__ X = a.X[ctx.pr];
     const float* __restrict__ Y = a.Y[ctx.pr];
-    const float2* __restrict__ X2 = reinterpret_cast<const float2*>(X);
-    const float2* __restrict__ Y2 = reinterpret_cast<const float2*>(Y);
-    float2* Xn2 = reinterpret_cast<float2*>(a.X[ctx.pr ^ 1]);
-    float2* Yn2 = reinterpret_cast<float2*>(a.Y[ctx.pr ^ 1]);
-    float4* V4 = reinterpret_cast<float4*>(a.V[ctx.pv]);
-    const float4* __restrict__ Rb4 = reinterpret_cast<const float4*>(a.Rb);
-    const int2* __restrict__ og2 = reinterpret_cast<const int2*>(a.orig[ctx.pv]);
+    const float2* __restrict__ V = a.V[ctx.pv];
+    const int* __restrict__ og = a.orig[ctx.pv];
     const int* __restrict__ cs = a.cell_start;
-    const int npairs = ctx.ntot >> 1;
-    const int npad = (npairs + 31) & ~31;
-
-    for (int base = blockIdx.x * CL_THREADS; base < npad; base += gsz) {
-        const int  p = base + tid;
-        const bool act = p < npairs;
-        float2 xi = make_float2(CL_SENT, CL_SENT), yi = xi;
-        float4 rb = make_float4(CL_SENT, CL_SENT, CL_SENT, CL_SENT);
-        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        int2 o = make_int2(-1, -1);
-        if (act) {
-            xi = X2[p]; yi = Y2[p]; rb = Rb4[p]; o = og2[p];
-            if (a.rc.nsteps > 0) v = V4[p];
-        }
-        const bool live0 = o.x >= 0, live1 = o.y >= 0;
-        int r = 1, b0 = CL_K, b1 = CL_K;
-        if (live0) {
-            r  = strip_coord(rb.y, a.inv_hy, a.nrows);
-            b0 = strip_coord(rb.x, a.inv_wx, a.nbx);
-            b1 = live1 ? strip_coord(rb.z, a.inv_wx, a.nbx) : b0;
-        }
-        const bool edge = (r == 0) | (r == a.nrows - 1) | (b0 < CL_K) | (b1 > a.nbx - 1 - CL_K);
-        const bool wedge = __any_sync(0xffffffffu, edge);
-        float F0x = 0.0f, F0y = 0.0f, F1x = 0.0f, F1y = 0.0f;
-        {
-            PairAcc acc;
-            acc.axA = acc.ayA = acc.axB = acc.ayB = acc.peA = acc.peB = make_float2(0.0f, 0.0f);
-            const float2 nxi = make_float2(-xi.x, -xi.y), nyi = make_float2(-yi.x, -yi.y);
-            const float2 nxs = make_float2(-xi.y, -xi.x), nys = make_float2(-yi.y, -yi.x);
-            if (!wedge) {
-                if (live0) {
-                    const int cl = r * a.nbx + b0 - CL_K, ch = r * a.nbx + b1 + CL_K + 1;
-                    const int s0 = cs[cl - a.nbx], e0 = cs[ch - a.nbx];
-                    const int s1 = cs[cl],         e1 = cs[ch];
-                    const int s2 = cs[cl + a.nbx], e2 = cs[ch + a.nbx];
-                    // the own row and the row below are needed ~1000 issue slots from now: start
-                    // their lines on the way to L1 while the first range is evaluated
-                    prefetch_l1(X2 + (s1 >> 1)); prefetch_l1(Y2 + (s1 >> 1));
-                    prefetch_l1(X2 + (e1 >> 1)); prefetch_l1(Y2 + (e1 >> 1));
-                    prefetch_l1(X2 + (s2 >> 1)); prefetch_l1(Y2 + (s2 >> 1));
-                    prefetch_l1(X2 + (e2 >> 1)); prefetch_l1(Y2 + (e2 >> 1));
-                    row_range<PE, false>(pc, c2, X2, Y2, s0 >> 1, (e0 + 1) >> 1, p, nxi, nyi, nxs, nys, acc);
-                    row_range<PE, true >(pc, c2, X2, Y2, s1 >> 1, (e1 + 1) >> 1, p, nxi, nyi, nxs, nys, acc);
-                    row_range<PE, false>(pc, c2, X2, Y2, s2 >> 1, (e2 + 1) >> 1, p, nxi, nyi, nxs, nys, acc);
-                }
-            } else if (live0) {
-                // bins [b0-K, b1+K] of rows r-1, r, r+1 with periodic wrap of both indices: one piece
-                // plus up to two wrapped pieces per row (the whole row once if the union would overlap)
-                int lo = b0 - CL_K, hi = b1 + CL_K;
-                if (hi - lo + 1 > a.nbx) { lo = 0; hi = a.nbx - 1; }
-#pragma unroll 1
-                for (int dr = -1; dr <= 1; ++dr) {
-                    int rr = r + dr;
-                    rr += (rr < 0) ? a.nrows : 0;
-                    rr -= (rr >= a.nrows) ? a.nrows : 0;
-                    const int* __restrict__ csr = cs + rr * a.nbx;
-#pragma unroll 1
-                    for (int piece = 0; piece < 3; ++piece) {
-                        int bl, bh;
-                        if (piece == 0)      { bl = max(lo, 0); bh = min(hi, a.nbx - 1); }
-                        else if (piece == 1) { if (lo >= 0) continue; bl = lo + a.nbx; bh = a.nbx - 1; }
-                        else                 { if (hi < a.nbx) continue; bl = 0; bh = hi - a.nbx; }
-                        edge_range<PE>(pc, c2, X2, Y2, csr[bl], csr[bh + 1], p, nxi, nyi, nxs, nys, acc);
-                    }
-                }
+    fence_proxy_async();
+    for (;;) {
+        // plan the next chunk (dependent index look-ups, ~4 L2 round trips) BEFORE waiting for a free
+        // stage: the look-ups overlap the consumers' work on the chunks in flight
+        const int c = atomicAdd(&a.sched[par], 1);
+        const bool last = (c >= ctx.nchunks);
+        int row = 0, slot0 = 0, n = 0, nent = 0;
+        int ws[3] = {0, 0, 0}, we[3] = {0, 0, 0}, cb[3] = {0, 0, 0}, nc[3] = {0, 0, 0};
+        bool direct = false;
+        if (!last) {
+            const int2 tab = a.chunk_tab[c];
+            row = tab.x; slot0 = tab.y;
+            const int rend = cs[(row + 1) * a.nbx];                    // next row's first slot (even)
+            n = min(CL_CH, rend - slot0);
+            const int bf = strip_coord(a.Rb[slot0].x, a.inv_wx, a.nbx);
+            const int bl = strip_coord(a.Rb[slot0 + n - 1].x, a.inv_wx, a.nbx);   // a pad clamps to the last bin
+            const int lo = max(bf - CL_K, 0), hi = min(bl + CL_K, a.nbx - 1);
+            nent = hi - lo + 2;                                        // cell_start entries lo .. hi+1
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                int rr = row + k - 1;
+                rr += (rr < 0) ? a.nrows : 0;
+                rr -= (rr >= a.nrows) ? a.nrows : 0;
+                const int c0 = rr * a.nbx + lo;
+                cb[k] = c0 & ~3;
+                nc[k] = ((c0 + nent + 3) & ~3) - cb[k];
+                ws[k] = cs[c0] & ~3;
+                we[k] = (cs[c0 + nent - 1] + 3) & ~3;
+                direct |= (we[k] - ws[k] > CL_WMAX) | (nc[k] > CL_CSMAX);
             }
-            // accumulators hold -F:  i0 <- straight.x + swapped.y,  i1 <- straight.y + swapped.x
-            F0x = -(acc.axA.x + acc.axB.y); F0y = -(acc.ayA.x + acc.ayB.y);
-            F1x = -(acc.axA.y + acc.axB.x); F1y = -(acc.ayA.y + acc.ayB.x);
-            if (PE) pe_thread += (acc.peA.x + acc.peB.y) + (acc.peA.y + acc.peB.x);
         }
-        if (!act) continue;
-        float2 v0 = make_float2(v.x, v.y), v1 = make_float2(v.z, v.w);
-        float2 xn = xi, yn = yi;
-        if (live0) moved |= finish_particle(a, fl, 2 * p, o.x, xi.x, yi.x, F0x, F0y, v0, make_float2(rb.x, rb.y), xn.x, yn.x, ke_thread);
-        if (live1) moved |= finish_particle(a, fl, 2 * p + 1, o.y, xi.y, yi.y, F1x, F1y, v1, make_float2(rb.z, rb.w), xn.y, yn.y, ke_thread);
-        if (a.rc.nsteps > 0 && !(fl.final && !fl.thermo)) {
-            V4[p] = make_float4(v0.x, v0.y, v1.x, v1.y);
-            if (!fl.thermo) { Xn2[p] = xn; Yn2[p] = yn; }
+        const int s = (int)(ctx.it % CL_NST);
+        const unsigned ph = (ctx.it / CL_NST) & 1u;
+        ++ctx.it;
+        mbar_wait(&empty[s], ph ^ 1u);
+        StageMeta& m = meta[s];
+        if (last) { m.chunk = -1; mbar_arrive(&full[s]); break; }
+        const int own0 = slot0 & ~3, nown = ((slot0 + n + 3) & ~3) - own0;
+        m.chunk = c; m.row = row; m.slot0 = slot0; m.n = n; m.direct = direct ? 1 : 0; m.own0 = own0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { m.ws[k] = ws[k]; m.cb[k] = cb[k]; }
+        if (direct) { mbar_arrive(&full[s]); continue; }
+        Stage& st = stages[s];
+        unsigned bytes = (unsigned)nown * (8u + 8u + 4u);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bytes += (unsigned)(we[k] - ws[k]) * 8u + (unsigned)nc[k] * 4u;
+        mbar_arrive_expect_tx(&full[s], bytes);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (we[k] > ws[k]) {
+                bulk_g2s(st.x[k], X + ws[k], (unsigned)(we[k] - ws[k]) * 4u, &full[s]);
+                bulk_g2s(st.y[k], Y + ws[k], (unsigned)(we[k] - ws[k]) * 4u, &full[s]);
+            }
+            bulk_g2s(st.cs[k], cs + cb[k], (unsigned)nc[k] * 4u, &full[s]);
         }
+        bulk_g2s(st.rb, a.Rb + own0, (unsigned)nown * 8u, &full[s]);
+        bulk_g2s(st.v, V + own0, (unsigned)nown * 8u, &full[s]);
+        bulk_g2s(st.og, og + own0, (unsigned)nown * 4u, &full[s]);
     }
 }
 
-__global__ void __launch_bounds__(CL_THREADS, CL_MINBLOCKS)
+// ---- consumers: forces + integrate of one chunk ----------------------------------------------------
+template <bool PE, bool STAGED>
+__device__ __forceinline__ void chunk_compute(const CellsArgs& a, const Ctx& ctx, const StepFlags& fl,
+                                              const StageMeta& m, const StageMeta& ms, const Stage& st,
+                                              float& pe_thread, float& ke_thread, int& moved) {
+    // m: register copy of the stage header; ms: the same header in shared memory (fields indexed at
+    // run time are read from there, not from a local-memory copy)
+    const int t = threadIdx.x;
+    const PairConsts pc = a.pc;
+    const PairConsts2 c2 = make_pair_consts2(pc);
+    const float2* __restrict__ X2g = reinterpret_cast<const float2*>(a.X[ctx.pr]);
+    const float2* __restrict__ Y2g = reinterpret_cast<const float2*>(a.Y[ctx.pr]);
+    float2* Xn2 = reinterpret_cast<float2*>(a.X[ctx.pr ^ 1]);
+    float2* Yn2 = reinterpret_cast<float2*>(a.Y[ctx.pr ^ 1]);
+    float4* V4 = reinterpret_cast<float4*>(a.V[ctx.pv]);
+    const int* __restrict__ csg = a.cell_start;
+    const int  p = (m.slot0 >> 1) + t;                 // global slot-pair index
+    const bool act = 2 * t < m.n;
+    float2 xi = make_float2(CL_SENT, CL_SENT), yi = xi;
+    float4 rb = make_float4(CL_SENT, CL_SENT, CL_SENT, CL_SENT);
+    float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    int2 o = make_int2(-1, -1);
+    if (act) {
+        if (STAGED) {
+            const int q = ((m.slot0 - m.own0) >> 1) + t;
+            rb = reinterpret_cast<const float4*>(st.rb)[q];
+            o  = reinterpret_cast<const int2*>(st.og)[q];
+            if (a.rc.nsteps > 0) v = reinterpret_cast<const float4*>(st.v)[q];
+            xi = reinterpret_cast<const float2*>(st.x[1])[p - (m.ws[1] >> 1)];
+            yi = reinterpret_cast<const float2*>(st.y[1])[p - (m.ws[1] >> 1)];
+        } else {
+            xi = X2g[p]; yi = Y2g[p];
+            rb = reinterpret_cast<const float4*>(a.Rb)[p];
+            o  = reinterpret_cast<const int2*>(a.orig[ctx.pv])[p];
+            if (a.rc.nsteps > 0) v = V4[p];
+        }
+    }
+    const bool live0 = o.x >= 0, live1 = o.y >= 0;
+    const int r = m.row;
+    int b0 = CL_K, b1 = CL_K;
+    if (live0) {
+        b0 = strip_coord(rb.x, a.inv_wx, a.nbx);
+        b1 = live1 ? strip_coord(rb.z, a.inv_wx, a.nbx) : b0;
+    }
+    const bool yedge = (r == 0) | (r == a.nrows - 1);
+    const bool edge = live0 & (yedge | (b0 < CL_K) | (b1 > a.nbx - 1 - CL_K));
+    const bool wedge = __any_sync(0xffffffffu, edge);
+    PairAcc acc;
+    acc.axA = acc.ayA = acc.axB = acc.ayB = acc.peA = acc.peB = make_float2(0.0f, 0.0f);
+    const float2 nxi = make_float2(-xi.x, -xi.y), nyi = make_float2(-yi.x, -yi.y);
+    const float2 nxs = make_float2(-xi.y, -xi.x), nys = make_float2(-yi.y, -yi.x);
+    if (!wedge) {
+        if (live0) {
+#pragma unroll 1
+            for (int k = 0; k < 3; ++k) {       // rows r-1, r, r+1: one contiguous range each
+                const int cl = (r + k - 1) * a.nbx + b0 - CL_K, ch = (r + k - 1) * a.nbx + b1 + CL_K + 1;
+                const int pself = (k == 1) ? p : -1;
+                if (STAGED) {
+                    const int cb = ms.cb[k], w2 = ms.ws[k] >> 1;
+                    const int s = st.cs[k][cl - cb], e = st.cs[k][ch - cb];
+                    const float2* xw = reinterpret_cast<const float2*>(st.x[k]) - w2;
+                    const float2* yw = reinterpret_cast<const float2*>(st.y[k]) - w2;
+                    row_range<PE>(pc, c2, xw, yw, s >> 1, (e + 1) >> 1, pself, nxi, nyi, nxs, nys, acc);
+                } else {
+                    const int s = csg[cl], e = csg[ch];
+                    row_range<PE>(pc, c2, X2g, Y2g, s >> 1, (e + 1) >> 1, pself, nxi, nyi, nxs, nys, acc);
+                }
+            }
+        }
+    } else if (live0) {
+        // bins [b0-K, b1+K] of rows r-1, r, r+1 with periodic wrap of both indices: one piece plus up
+        // to two wrapped pieces per row (the whole row once if the union would overlap itself).
+        // The unwrapped piece lies inside the staged window; wrapped pieces are read from global.
+        int lo = b0 - CL_K, hi = b1 + CL_K;
+        const bool whole = (hi - lo + 1 > a.nbx);
+        if (whole) { lo = 0; hi = a.nbx - 1; }
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {
+            int rr = r + k - 1;
+            rr += (rr < 0) ? a.nrows : 0;
+            rr -= (rr >= a.nrows) ? a.nrows : 0;
+            const int* __restrict__ csr = csg + rr * a.nbx;
+            {
+                const int bl = max(lo, 0), bh = min(hi, a.nbx - 1);
+                if (STAGED && !whole) {
+                    const int cb = ms.cb[k], w2 = ms.ws[k] >> 1;
+                    const int s = st.cs[k][rr * a.nbx + bl - cb], e = st.cs[k][rr * a.nbx + bh + 1 - cb];
+                    const float2* xw = reinterpret_cast<const float2*>(st.x[k]) - w2;
+                    const float2* yw = reinterpret_cast<const float2*>(st.y[k]) - w2;
+                    edge_range<PE>(pc, c2, xw, yw, s, e, p, nxi, nyi, nxs, nys, acc);
+                } else {
+                    edge_range<PE>(pc, c2, X2g, Y2g, csr[bl], csr[bh + 1], p, nxi, nyi, nxs, nys, acc);
+                }
+            }
+            if (lo < 0)      edge_range<PE>(pc, c2, X2g, Y2g, csr[lo + a.nbx], csr[a.nbx], p, nxi, nyi, nxs, nys, acc);
+            if (hi >= a.nbx) edge_range<PE>(pc, c2, X2g, Y2g, csr[0], csr[hi - a.nbx + 1], p, nxi, nyi, nxs, nys, acc);
+        }
+    }
+    // accumulators hold -F:  i0 <- straight.x + swapped.y,  i1 <- straight.y + swapped.x
+    const float F0x = -(acc.axA.x + acc.axB.y), F0y = -(acc.ayA.x + acc.ayB.y);
+    const float F1x = -(acc.axA.y + acc.axB.x), F1y = -(acc.ayA.y + acc.ayB.x);
+    if (PE) pe_thread += (acc.peA.x + acc.peB.y) + (acc.peA.y + acc.peB.x);
+    if (!act) return;
+    float2 v0 = make_float2(v.x, v.y), v1 = make_float2(v.z, v.w);
+    float2 xn = xi, yn = yi;
+    if (live0) moved |= finish_particle(a, fl, 2 * p, o.x, xi.x, yi.x, F0x, F0y, v0, make_float2(rb.x, rb.y), xn.x, yn.x, ke_thread);
+    if (live1) moved |= finish_particle(a, fl, 2 * p + 1, o.y, xi.y, yi.y, F1x, F1y, v1, make_float2(rb.z, rb.w), xn.y, yn.y, ke_thread);
+    if (a.rc.nsteps > 0 && !(fl.final && !fl.thermo)) {
+        V4[p] = make_float4(v0.x, v0.y, v1.x, v1.y);
+        if (!fl.thermo) { Xn2[p] = xn; Yn2[p] = yn; }
+    }
+}
+
+template <bool PE>
+__device__ __forceinline__ void consume_step(const CellsArgs& a, Ctx& ctx, const StepFlags& fl,
+                                             const Stage* stages, const StageMeta* meta,
+                                             unsigned long long* full, unsigned long long* empty,
+                                             float* sred, int par, bool want_ke, int& moved) {
+    for (;;) {
+        const int s = (int)(ctx.it % CL_NST);
+        const unsigned ph = (ctx.it / CL_NST) & 1u;
+        ++ctx.it;
+        mbar_wait(&full[s], ph);
+        const StageMeta m = meta[s];
+        if (m.chunk >= 0) {
+            float pe_thread = 0.0f, ke_thread = 0.0f;
+            if (m.direct) chunk_compute<true, false>(a, ctx, fl, m, meta[s], stages[s], pe_thread, ke_thread, moved);
+            else          chunk_compute<PE, true >(a, ctx, fl, m, meta[s], stages[s], pe_thread, ke_thread, moved);
+            // per-chunk energy partials, reduced in chunk order after the barrier: independent of
+            // which CTA ran the chunk
+            if (PE) {
+                const float tsum = consumer_sum(pe_thread, sred);
+                if (threadIdx.x == 0) __stcg(&a.pe_part[par * a.maxchunks + m.chunk], tsum);
+            }
+            if (want_ke) {
+                const float tsum = consumer_sum(ke_thread, sred);
+                if (threadIdx.x == 0) __stcg(&a.ke_part[par * a.maxchunks + m.chunk], tsum);
+            }
+        }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);
+        if (m.chunk < 0) break;
+    }
+}
+
+extern __shared__ __align__(128) unsigned char cells_smem[];
+
+__global__ void __launch_bounds__(CL_THREADS, 2)
 cells_persistent_kernel(const CellsArgs a) {
-    __shared__ int   sscan[CL_THREADS / 32 + 1];
-    __shared__ float sred[CL_THREADS / 32];
-    __shared__ float s_lambda;
+    __shared__ int    sscan[CL_THREADS / 32 + 1];
+    __shared__ float  sred[CL_THREADS / 32];
+    __shared__ double sdbl[CL_THREADS / 32];
+    __shared__ float  s_lambda;
     __shared__ long long s_pt[12];
+    __shared__ __align__(8) unsigned long long s_full[CL_NST], s_empty[CL_NST];
+    __shared__ StageMeta s_meta[CL_NST];
+    Stage* stages = reinterpret_cast<Stage*>(cells_smem);
     const int tid = threadIdx.x, gtid = blockIdx.x * CL_THREADS + tid, gsz = a.G * CL_THREADS;
+    const bool producer = tid >= CL_CONSUMERS;
     const RunCtl rc = a.rc;
     Ctx ctx;
     ctx.epoch = 0;
+    ctx.it = 0;
     ctx.pt = a.prof ? s_pt : nullptr;
-    if (ctx.pt && tid == 0) { for (int k = 0; k < 11; ++k) s_pt[k] = 0; s_pt[11] = clock64(); }
+    if (tid == 0) {
+        if (ctx.pt) { for (int k = 0; k < 11; ++k) s_pt[k] = 0; s_pt[11] = clock64(); }
+        for (int k = 0; k < CL_NST; ++k) { mbar_init(&s_full[k], 1); mbar_init(&s_empty[k], CL_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     ctx.pr = a.state[ST_PR];
     ctx.pv = a.state[ST_PV];
     ctx.ntot = a.state[ST_NTOT];
+    ctx.nchunks = a.state[ST_NCHUNKS];
 
     if (a.s_begin < 0) {
         // load the caller's state (original order, no pads) and sort it
@@ -548,7 +778,7 @@ cells_persistent_kernel(const CellsArgs a) {
         CL_BARRIER();
         cells_rebuild(a, ctx, sscan);
         if (a.mode == 1) {
-            // neighbour recount through the same ranges (generic path), original order out
+            // neighbour recount through the same ranges (scalar path), original order out
             const float* X = a.X[ctx.pr];
             const float* Y = a.Y[ctx.pr];
             const int* og = a.orig[ctx.pv];
@@ -583,27 +813,21 @@ cells_persistent_kernel(const CellsArgs a) {
         if (s > a.s_begin || a.s_begin >= 0) {
             if (__ldcg(a.state + ST_FLAG) == (int)(s + 1)) cells_rebuild(a, ctx, sscan);
         }
-        float ke_thread = 0.0f, pe_thread = 0.0f;
-        int   moved = 0;
-        if (want_pe) force_pass<true >(a, ctx, fl, pe_thread, ke_thread, moved);
-        else         force_pass<false>(a, ctx, fl, pe_thread, ke_thread, moved);
-
-        if (want_pe) {
-            float t = block_sum<CL_THREADS>(pe_thread, sred);
-            if (tid == 0) __stcg(&a.pe_part[par * a.G + blockIdx.x], t);
-        }
-        if (fl.want_e || fl.thermo) {
-            float t = block_sum<CL_THREADS>(ke_thread, sred);
-            if (tid == 0) __stcg(&a.ke_part[par * a.G + blockIdx.x], t);
+        // the other parity's chunk counter is idle during this step: clear it for the next one
+        if (gtid == 0) __stcg(&a.sched[par ^ 1], 0);
+        int moved = 0;
+        if (producer) {
+            if (tid == CL_CONSUMERS) produce_step(a, ctx, stages, s_meta, s_full, s_empty, par);
+            ctx.it = __shfl_sync(0xffffffffu, ctx.it, 0);
+        } else {
+            const bool want_ke = fl.want_e || fl.thermo;
+            if (want_pe) consume_step<true >(a, ctx, fl, stages, s_meta, s_full, s_empty, sred, par, want_ke, moved);
+            else         consume_step<false>(a, ctx, fl, stages, s_meta, s_full, s_empty, sred, par, want_ke, moved);
         }
         if (fl.thermo) {
             CL_BARRIER();
-            if (tid < 32) {
-                double ke2 = 0.0;
-                for (int k = tid; k < a.G; k += 32) ke2 += (double)__ldcg(&a.ke_part[par * a.G + k]);
-                ke2 = warp_sum(ke2);
-                if (tid == 0) s_lambda = sqrtf(rc.thermo_kT / ((float)(0.5 * ke2) / (float)a.N));
-            }
+            const double ke2 = block_sum_array(a.ke_part + par * a.maxchunks, ctx.nchunks, sdbl);
+            if (tid == 0) s_lambda = sqrtf(rc.thermo_kT / ((float)(0.5 * ke2) / (float)a.N));
             __syncthreads();
             const float lam = s_lambda;
             const float* X = a.X[ctx.pr];
@@ -643,14 +867,10 @@ cells_persistent_kernel(const CellsArgs a) {
         CL_BARRIER();
         CL_PROF(1);
 
-        if (blockIdx.x == 0 && tid < 32 && want_pe) {
-            double pe2 = 0.0, ke2 = 0.0;
-            for (int k = tid; k < a.G; k += 32) {
-                pe2 += (double)__ldcg(&a.pe_part[par * a.G + k]);
-                if (fl.want_e) ke2 += (double)__ldcg(&a.ke_part[par * a.G + k]);
-            }
-            pe2 = warp_sum(pe2);
-            ke2 = warp_sum(ke2);
+        if (blockIdx.x == 0 && want_pe) {
+            const double pe2 = block_sum_array(a.pe_part + par * a.maxchunks, ctx.nchunks, sdbl);
+            double ke2 = 0.0;
+            if (fl.want_e) ke2 = block_sum_array(a.ke_part + par * a.maxchunks, ctx.nchunks, sdbl);
             if (tid == 0) {
                 if (fl.want_e) {
                     float* o = rc.ke_pe + 2 * (s / rc.energy_every);
@@ -662,7 +882,9 @@ cells_persistent_kernel(const CellsArgs a) {
             }
         }
     }
-    if (gtid == 0) { a.state[ST_PR] = ctx.pr; a.state[ST_PV] = ctx.pv; a.state[ST_NTOT] = ctx.ntot; }
+    if (gtid == 0) {
+        a.state[ST_PR] = ctx.pr; a.state[ST_PV] = ctx.pv; a.state[ST_NTOT] = ctx.ntot;
+    }
     if (ctx.pt && tid == 0)
         for (int k = 0; k < 11; ++k) a.prof[blockIdx.x * 12 + k] = s_pt[k];
 }
@@ -688,7 +910,10 @@ struct Cells {
     float2 *V[2] = {nullptr, nullptr}, *Rb = nullptr, *Fs = nullptr;
     int *orig[2] = {nullptr, nullptr};
     int *key = nullptr, *rank = nullptr, *tmp = nullptr, *cell_count = nullptr, *cell_start = nullptr,
-        *row_tot = nullptr;
+        *row_tot = nullptr, *sched = nullptr;
+    int2* chunk_tab = nullptr;
+    int maxchunks = 0;
+    size_t smem = 0;
     float *pe_part = nullptr, *ke_part = nullptr;
     int* state = nullptr;
     unsigned* bar = nullptr;
@@ -720,12 +945,15 @@ int cells_create(ljmd_handle* h) {
     cl->inv_wx = (float)cl->nbx / h->p.box;
     cl->Nalloc = (int)(((N + cl->nrows + 63) / 64) * 64 + 64);
 
+    cl->maxchunks = (int)(N / CL_CH + cl->nrows + 2);
+    cl->smem = sizeof(Stage) * CL_NST;
+    LJ_CUDA(cudaFuncSetAttribute(cells_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl->smem));
     int per_sm = 0;
-    LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cells_persistent_kernel, CL_THREADS, 0));
+    LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cells_persistent_kernel, CL_THREADS, cl->smem));
     if (per_sm < 1) { set_error("cell-list kernel does not fit on an SM"); return LJMD_E_STATE; }
     if (const char* e = getenv("LJMD_CELLS_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));
     long long g = (long long)per_sm * h->num_sms;
-    g = std::min<long long>(g, std::max<long long>(1, (N / 2 + CL_THREADS - 1) / CL_THREADS));
+    g = std::min<long long>(g, std::max<long long>(1, (N + CL_CH - 1) / CL_CH));
     cl->G = (int)g;
 
     const size_t na = (size_t)cl->Nalloc;
@@ -742,10 +970,13 @@ int cells_create(ljmd_handle* h) {
     LJ_CUDA(cudaMalloc(&cl->tmp, sizeof(int) * na));
     LJ_CUDA(cudaMalloc(&cl->cell_count, sizeof(int) * (size_t)cl->ncells));
     LJ_CUDA(cudaMemset(cl->cell_count, 0, sizeof(int) * (size_t)cl->ncells));
-    LJ_CUDA(cudaMalloc(&cl->cell_start, sizeof(int) * ((size_t)cl->ncells + 1)));
+    LJ_CUDA(cudaMalloc(&cl->cell_start, sizeof(int) * ((size_t)cl->ncells + 1 + 8)));   // + bulk-copy round-up
+    LJ_CUDA(cudaMemset(cl->cell_start, 0, sizeof(int) * ((size_t)cl->ncells + 1 + 8)));
     LJ_CUDA(cudaMalloc(&cl->row_tot, sizeof(int) * (size_t)cl->nrows));
-    LJ_CUDA(cudaMalloc(&cl->pe_part, sizeof(float) * 2 * cl->G));
-    LJ_CUDA(cudaMalloc(&cl->ke_part, sizeof(float) * 2 * cl->G));
+    LJ_CUDA(cudaMalloc(&cl->chunk_tab, sizeof(int2) * (size_t)cl->maxchunks));
+    LJ_CUDA(cudaMalloc(&cl->sched, sizeof(int) * 2));
+    LJ_CUDA(cudaMalloc(&cl->pe_part, sizeof(float) * 2 * cl->maxchunks));
+    LJ_CUDA(cudaMalloc(&cl->ke_part, sizeof(float) * 2 * cl->maxchunks));
     LJ_CUDA(cudaMalloc(&cl->state, sizeof(int) * ST_WORDS));
     LJ_CUDA(cudaMemset(cl->state, 0, sizeof(int) * ST_WORDS));
     LJ_CUDA(cudaMalloc(&cl->bar, sizeof(unsigned)));
@@ -759,6 +990,7 @@ void cells_destroy(ljmd_handle* h) {
     for (int k = 0; k < 2; ++k) { cudaFree(cl->X[k]); cudaFree(cl->Y[k]); cudaFree(cl->V[k]); cudaFree(cl->orig[k]); }
     cudaFree(cl->Rb); cudaFree(cl->Fs); cudaFree(cl->key); cudaFree(cl->rank); cudaFree(cl->tmp);
     cudaFree(cl->cell_count); cudaFree(cl->cell_start); cudaFree(cl->row_tot);
+    cudaFree(cl->chunk_tab); cudaFree(cl->sched);
     cudaFree(cl->pe_part); cudaFree(cl->ke_part);
     cudaFree(cl->state); cudaFree(cl->bar); cudaFree(cl->prof);
     delete cl;
@@ -777,6 +1009,7 @@ static void fill_args(ljmd_handle* h, CellsArgs& a) {
     a.Rb = cl->Rb; a.Fs = cl->Fs;
     a.key = cl->key; a.rank = cl->rank; a.tmp = cl->tmp;
     a.cell_count = cl->cell_count; a.cell_start = cl->cell_start; a.row_tot = cl->row_tot;
+    a.chunk_tab = cl->chunk_tab; a.sched = cl->sched; a.maxchunks = cl->maxchunks;
     a.pe_part = cl->pe_part; a.ke_part = cl->ke_part;
     a.state = cl->state; a.bar = cl->bar; a.prof = cl->prof;
 }
@@ -784,9 +1017,10 @@ static void fill_args(ljmd_handle* h, CellsArgs& a) {
 static int launch(ljmd_handle* h, CellsArgs& a) {
     Cells* cl = h->cells;
     LJ_CUDA(cudaMemsetAsync(cl->bar, 0, sizeof(unsigned), h->stream));
+    LJ_CUDA(cudaMemsetAsync(cl->sched, 0, sizeof(int) * 2, h->stream));
     void* args[] = {(void*)&a};
     LJ_CUDA(cudaLaunchCooperativeKernel((void*)cells_persistent_kernel, dim3(cl->G), dim3(CL_THREADS),
-                                        args, 0, h->stream));
+                                        args, cl->smem, h->stream));
     h->launches++;
     return 0;
 }
@@ -800,7 +1034,7 @@ int cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_
         LJ_CUDA(cudaMemsetAsync(rc.traj, 0, sizeof(float2) * N * rc.S, st));      // MD:89
     // fresh call: parities 0, rebuild counter 0, flag 0 (the error word is sticky)
     LJ_CUDA(cudaMemsetAsync(cl->state, 0, sizeof(int) * 3, st));
-    LJ_CUDA(cudaMemsetAsync(cl->state + ST_FLAG, 0, sizeof(int) * 2, st));
+    LJ_CUDA(cudaMemsetAsync(cl->state + ST_FLAG, 0, sizeof(int) * 3, st));
     CellsArgs a{};
     fill_args(h, a);
     a.R_in = R_in; a.V_in = V_in;
@@ -864,7 +1098,7 @@ int cells_neighbor_count(ljmd_handle* h, const float2* R, float radius, int* nbr
         return LJMD_E_INVALID;
     }
     LJ_CUDA(cudaMemsetAsync(cl->state, 0, sizeof(int) * 3, h->stream));
-    LJ_CUDA(cudaMemsetAsync(cl->state + ST_FLAG, 0, sizeof(int) * 2, h->stream));
+    LJ_CUDA(cudaMemsetAsync(cl->state + ST_FLAG, 0, sizeof(int) * 3, h->stream));
     CellsArgs a{};
     fill_args(h, a);
     a.R_in = R; a.V_in = nullptr;
