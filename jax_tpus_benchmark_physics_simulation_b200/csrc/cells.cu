@@ -12,8 +12,8 @@
 // vectorised position loads (9 narrow bins per row = 42 candidates/particle at rho 0.8, against 57
 // for square 3x3 cells) and the rebuild is only a counting sort.
 //
-// Data layout in HBM (all in cell-sorted "slot" order; every row starts on an even slot, a row with
-// an odd population is padded with one sentinel slot, so slots pair up as aligned float2):
+// Data layout in HBM (all in cell-sorted "slot" order; every row starts on a multiple of 4 slots and
+// is padded with sentinel slots, so slots pair up as aligned float2 and bulk copies stay 16-byte aligned):
 //   X[2], Y[2]  float   positions, structure-of-arrays, ping-pong by step (the buffer being read is
 //                        never written in a step).  One 64-bit load = the x of two adjacent slots
 //                        = one operand of the packed FP32x2 pipe.
@@ -24,18 +24,18 @@
 //   cell_start  int32   prefix-sum cell index over nrows*nbx cells (+1)
 //
 // One PERSISTENT cooperative kernel runs a whole ljmd_run().  Per step ONE pass over the state and
-// one grid barrier.  A row is cut into chunks of 512 slots; a CTA is 8 consumer warps + 1 producer
-// warp.  The producer runs one chunk ahead: it looks up the chunk's three row windows and issues
-// TMA bulk copies (cp.async.bulk, mbarrier complete_tx) of everything the chunk needs — the x / y
-// windows of rows r-1, r, r+1, the matching slices of the cell index, and the chunk's own Rb / V /
-// orig — into a 2-stage shared-memory ring; the consumers (each thread owns two adjacent slots)
-// evaluate forces from shared memory only, then velocity-Verlet + energies + displacement test and
-// write the new state: each particle's state is read once and written once per step and no load
-// in the pair loop can miss.  Chunks are handed out dynamically (one atomic per chunk); energies
-// are per-chunk partials reduced in chunk order, so results do not depend on the schedule.
+// one grid barrier.  A row is cut into units of 64 slots = one warp (each thread owns two adjacent
+// slots).  Every warp is its own producer and consumer: before it evaluates unit u it issues the TMA
+// bulk copies (cp.async.bulk, mbarrier complete_tx) of everything unit u+1 needs — the x / y windows
+// of rows r-1, r, r+1, the matching slices of the cell index and the unit's own Rb — into its private
+// 2-stage shared-memory ring, from a per-unit copy plan that the rebuild precomputes.  The pair loop
+// reads shared memory only (no load in it can miss), then velocity-Verlet + energies + displacement
+// test and the new state is written: each particle's state is read once and written once per step.
+// Warps never wait for each other inside a step.  Energies are per-unit partials reduced in unit
+// order (deterministic).
 // The rebuild (bin + histogram with rank capture -> row-structured prefix sum -> scatter ->
-// deterministic in-cell order by original index + gather) runs inside the same kernel under a
-// grid-uniform condition: no host round trip (MD:82,103).
+// deterministic in-cell order by original index + gather -> copy plans) runs inside the same kernel
+// under a grid-uniform condition: no host round trip (MD:82,103).
 #include "ljmd_device.cuh"
 
 #include <algorithm>
@@ -45,14 +45,19 @@ namespace ljmd {
 
 namespace {
 
-constexpr int   CL_CONSUMERS = 256;               // consumer threads: one slot pair each
-constexpr int   CL_THREADS   = CL_CONSUMERS + 32;  // + one producer warp
-constexpr int   CL_CH        = 2 * CL_CONSUMERS;   // slots per chunk
-constexpr int   CL_NST       = 2;                  // stages of the shared-memory ring
-constexpr int   CL_WMAX      = 896;                // staged window capacity per row (slots): a lattice
-                                                   // row of 3 lattice lines beside one of 2 needs 1.5 * CL_CH
-constexpr int   CL_CSMAX     = 512;                // staged cell-index slice capacity per row
-// (2 CTAs x 9 warps per SM: one sub-partition hosts 5 warps, which caps the kernel at 96 registers)
+#ifndef LJMD_CELLS_UNROLL
+#define LJMD_CELLS_UNROLL 2
+#endif
+#ifndef LJMD_CELLS_MINBLOCKS
+#define LJMD_CELLS_MINBLOCKS 2
+#endif
+constexpr int   CL_UNROLL  = LJMD_CELLS_UNROLL;
+constexpr int   CL_THREADS = 256;                  // 8 warps, each with a private TMA ring
+constexpr int   CL_WARPS   = CL_THREADS / 32;
+constexpr int   CL_UNIT    = 64;                   // slots per unit (one warp, two slots per thread)
+constexpr int   CL_NST     = 2;                    // stages of a warp's ring
+constexpr int   CL_WMAX    = 160;                  // staged window capacity per row (slots): a lattice
+                                                   // row of 3 lattice lines beside one of 2 needs 1.5 units
 constexpr int   CL_K       = 4;        // bins per (rc + skin)
 constexpr int   CL_ORDER_MAX = 64;     // cells denser than this keep arrival order (see B5)
 // Pad slots sit far outside any box, each at its OWN place (pad_x): two pads must never coincide,
@@ -61,30 +66,32 @@ constexpr int   CL_ORDER_MAX = 64;     // cells denser than this keep arrival or
 constexpr float CL_SENT    = 1.0e8f;
 
 #ifndef LJMD_CELLS_RCP_PRODUCT
-#define LJMD_CELLS_RCP_PRODUCT 1       // one MUFU.RCP per TWO pairs (1/(a*b) trick), see eval_set
+#define LJMD_CELLS_RCP_PRODUCT 0       // 1: one MUFU.RCP per TWO pairs (1/(a*b) trick), see eval_set
 #endif
 
-enum { ST_PR = 0, ST_PV = 1, ST_REBUILDS = 2, ST_ERR = 3, ST_FLAG = 4, ST_NTOT = 5, ST_NCHUNKS = 6,
+enum { ST_PR = 0, ST_PV = 1, ST_REBUILDS = 2, ST_ERR = 3, ST_FLAG = 4, ST_NTOT = 5, ST_NUNITS = 6,
        ST_WORDS = 8 };
-
-// one stage of the ring: everything a chunk's consumers read (all 16-byte aligned for the bulk copies)
-struct __align__(16) Stage {
-    float  x[3][CL_WMAX];          // x window of rows r-1, r, r+1
-    float  y[3][CL_WMAX];
-    float2 rb[CL_CH + 4];          // own build positions, velocities, original indices
-    float2 v[CL_CH + 4];
-    int    og[CL_CH + 4];
-    int    cs[3][CL_CSMAX];        // cell_start slices of the three rows
-};
-struct StageMeta {
-    int chunk;                     // chunk id, -1 = end of step
-    int row, slot0, n;             // row, first slot, number of slots (even)
-    int direct;                    // 1 = windows too large for the stage: consumers read global memory
-    int ws[3];                     // first staged slot of each window   (multiple of 4)
-    int cb[3];                     // first staged cell of each cs slice (multiple of 4)
-    int own0;                      // first staged slot of rb / v / og   (multiple of 4)
-};
 enum { CERR_BARRIER = 1 };
+
+// copy plan of one unit, precomputed by the rebuild (32 bytes)
+struct __align__(16) UnitPlan {
+    int row, slot0, n, direct;     // row, first slot, number of slots (even); direct = 1: windows too
+                                   // large for a stage, the unit reads global memory
+    int ws[3];                     // first staged slot of each window   (multiple of 4)
+    int nw01;                      // staged slots of windows 0 and 1    (multiples of 4, 16 bits each)
+    // (the size of window 2 travels in the upper half of `n`)
+};
+// candidate ranges of one thread (= two adjacent slots), precomputed by the rebuild: for each stencil
+// row the slot-PAIR range [m0, m1) relative to the unit's staged window, one byte each, plus flags
+//   .x = m0_0 | m1_0 << 8 | m0_1 << 16 | m1_1 << 24     .y = m0_2 | m1_2 << 8 | flags << 16
+enum { PR_LIVE0 = 1, PR_LIVE1 = 2, PR_EDGE = 4 };
+// one stage of a warp's ring (all 16-byte aligned for the bulk copies)
+struct __align__(16) Stage {
+    float    x[3][CL_WMAX];        // x window of rows r-1, r, r+1
+    float    y[3][CL_WMAX];
+    uint2    pr[32];               // the 32 threads' candidate ranges
+    UnitPlan plan;                 // written by lane 0 before it issues the copies
+};
 
 struct CellsArgs {
     PairConsts pc;
@@ -98,10 +105,12 @@ struct CellsArgs {
     float2* Rb;
     float2* Fs;                     // forces held across the thermostat barrier
     int *key, *rank, *tmp, *cell_count, *cell_start, *row_tot;
-    int2*   chunk_tab;              // (row, first slot) of every chunk
-    int*    sched;                  // [2] dynamic chunk counters (by step parity)
-    int     maxchunks;
-    float  *pe_part, *ke_part;      // [2*maxchunks] per-chunk partials (by step parity)
+    int2*     unit_tab;             // (row, first slot) of every unit
+    UnitPlan* plans;                // copy plan of every unit
+    int*      sched;                // [2] dynamic unit counters (by step parity)
+    uint2*    pranges;              // candidate ranges of every slot pair
+    int       maxunits;
+    float  *pe_part, *ke_part;      // [2*maxunits] per-unit partials (by step parity)
     int*      state;                // ST_* words
     unsigned* bar;
     const float2* R_in;
@@ -156,8 +165,9 @@ __device__ __forceinline__ int block_exscan(int v, int* swarp /* CL_THREADS/32 +
 
 struct Ctx {
     unsigned epoch;
-    unsigned it;        // ring iteration counter (same in producer and consumers)
-    int pr, pv, ntot, nchunks;
+    unsigned uses;      // this warp's ring: units consumed so far (stage = uses % CL_NST)
+    unsigned phase;     // bit s = parity of the next completion of stage s's mbarrier
+    int pr, pv, ntot, nunits;
     long long* pt;      // shared-memory phase clocks (thread 0), or nullptr
 };
 
@@ -203,8 +213,8 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan) {
     }
     CL_BARRIER();
     CL_PROF(3);
-    // B3: row offsets (every row starts on an even slot) + in-row exclusive scan -> cell_start;
-    //     an odd row gets one sentinel pad slot; the row's counters are cleared for the next rebuild.
+    // B3: row offsets (every row starts on a multiple of 4 slots) + in-row exclusive scan ->
+    //     cell_start; the row is padded with sentinel slots; its counters are cleared for the next rebuild.
     {
         float* Xn = a.X[ctx.pr ^ 1];
         float* Yn = a.Y[ctx.pr ^ 1];
@@ -212,20 +222,20 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan) {
         for (int r = blockIdx.x; r < a.nrows; r += a.G) {
             int s = 0, sc = 0;
             for (int q = tid; q < r; q += CL_THREADS) {
-                const int len = (a.row_tot[q] + 1) & ~1;
+                const int len = (a.row_tot[q] + 3) & ~3;
                 s += len;
-                sc += (len + CL_CH - 1) / CL_CH;
+                sc += (len + CL_UNIT - 1) / CL_UNIT;
             }
             int carry, chunk0;
             (void)block_exscan(s, sscan, &carry);
             (void)block_exscan(sc, sscan, &chunk0);
             const int rtot = a.row_tot[r];
             const int row0 = carry;
-            // the row's chunks: consecutive runs of CL_CH slots, never straddling a row
+            // the row's units: consecutive runs of CL_UNIT slots, never straddling a row
             {
-                const int len = (rtot + 1) & ~1, nch = (len + CL_CH - 1) / CL_CH;
-                for (int j = tid; j < nch; j += CL_THREADS) a.chunk_tab[chunk0 + j] = make_int2(r, row0 + j * CL_CH);
-                if (r == a.nrows - 1 && tid == 0) a.state[ST_NCHUNKS] = chunk0 + nch;
+                const int len = (rtot + 3) & ~3, nch = (len + CL_UNIT - 1) / CL_UNIT;
+                for (int j = tid; j < nch; j += CL_THREADS) a.unit_tab[chunk0 + j] = make_int2(r, row0 + j * CL_UNIT);
+                if (r == a.nrows - 1 && tid == 0) a.state[ST_NUNITS] = chunk0 + nch;
             }
             for (int bb = 0; bb < a.nbx; bb += CL_THREADS) {
                 const int b = bb + tid;
@@ -236,16 +246,15 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan) {
                 if (b < a.nbx) a.cell_start[r * a.nbx + b] = carry + ex;
                 carry += tot;
             }
-            if (tid == 0) {
-                if (rtot & 1) {
-                    const int pad = row0 + rtot;
-                    a.tmp[pad] = -1; on[pad] = -1;
-                    Xn[pad] = pad_x(r, a.nrows); Yn[pad] = CL_SENT;
-                    a.Rb[pad] = make_float2(CL_SENT, CL_SENT);
-                    a.V[ctx.pv ^ 1][pad] = make_float2(0.0f, 0.0f);
-                }
-                if (r == a.nrows - 1) a.cell_start[a.ncells] = row0 + ((rtot + 1) & ~1);
+            // pad the row to a multiple of 4 slots with sentinel slots, each at its own place
+            if (tid < ((rtot + 3) & ~3) - rtot) {
+                const int pad = row0 + rtot + tid;
+                a.tmp[pad] = -1; on[pad] = -1;
+                Xn[pad] = pad_x(r, a.nrows); Yn[pad] = CL_SENT * (1.0f + 0.125f * (float)tid);
+                a.Rb[pad] = make_float2(CL_SENT, CL_SENT);
+                a.V[ctx.pv ^ 1][pad] = make_float2(0.0f, 0.0f);
             }
+            if (r == a.nrows - 1 && tid == 0) a.cell_start[a.ncells] = row0 + ((rtot + 3) & ~3);
         }
     }
     CL_BARRIER();
@@ -295,13 +304,82 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan) {
             on[d] = orig_old[ksel];
         }
         ctx.ntot = ntot_new;
-        ctx.nchunks = __ldcg(a.state + ST_NCHUNKS);
+        ctx.nunits = __ldcg(a.state + ST_NUNITS);
     }
     ctx.pr ^= 1;
     ctx.pv ^= 1;
     if (blockIdx.x == 0 && tid == 0) a.state[ST_REBUILDS] += 1;
     CL_BARRIER();
     CL_PROF(6);
+    // B6: per unit (one warp each) the copy plan, per thread of the unit its candidate ranges: both
+    //     depend only on the build-time structure, so the per-step pass does no index arithmetic.
+    //     Window k = bins [bf-K, bl+K] of row r+k-1 (periodic in r, clipped in x), aligned outwards
+    //     to 4 slots; a thread's range k = bins [b0-K, b1+K] of that row, as slot pairs relative to
+    //     the window.  Edge threads (wrapped ranges) and oversized units are flagged instead.
+    {
+        const int* __restrict__ cs = a.cell_start;
+        const int lane = tid & 31;
+        const int W = a.G * CL_WARPS, gw = blockIdx.x * CL_WARPS + (tid >> 5);
+        for (int u = gw; u < ctx.nunits; u += W) {
+            const int2 tab = a.unit_tab[u];
+            const int row = tab.x, slot0 = tab.y;
+            const int rend = cs[(row + 1) * a.nbx];                    // next row's first slot (even)
+            const int n = min(CL_UNIT, rend - slot0);
+            const int bf = strip_coord(a.Rb[slot0].x, a.inv_wx, a.nbx);
+            const int bl = strip_coord(a.Rb[slot0 + n - 1].x, a.inv_wx, a.nbx);   // a pad clamps to the last bin
+            const int lo = max(bf - CL_K, 0), hi = min(bl + CL_K, a.nbx - 1);
+            int ws[3], nw[3];
+            bool direct = false;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                int rr = row + k - 1;
+                rr += (rr < 0) ? a.nrows : 0;
+                rr -= (rr >= a.nrows) ? a.nrows : 0;
+                ws[k] = cs[rr * a.nbx + lo] & ~3;
+                nw[k] = ((cs[rr * a.nbx + hi + 1] + 3) & ~3) - ws[k];
+                direct |= (nw[k] > CL_WMAX);
+            }
+            if (lane == 0) {
+                UnitPlan pl;
+                pl.row = row; pl.slot0 = slot0; pl.direct = direct ? 1 : 0;
+                pl.n = n | (direct ? 0 : nw[2] << 16);
+                pl.ws[0] = ws[0]; pl.ws[1] = ws[1]; pl.ws[2] = ws[2];
+                pl.nw01 = direct ? 0 : (nw[0] | nw[1] << 16);
+                a.plans[u] = pl;
+            }
+            // this lane's slot pair
+            const int p = (slot0 >> 1) + lane;
+            if (2 * lane < n) {
+                const float4 rb = reinterpret_cast<const float4*>(a.Rb)[p];
+                const bool live0 = rb.x < 0.5f * CL_SENT, live1 = rb.z < 0.5f * CL_SENT;
+                unsigned flags = (live0 ? PR_LIVE0 : 0) | (live1 ? PR_LIVE1 : 0);
+                uint2 w = make_uint2(0u, 0u);
+                if (live0) {
+                    const int b0 = strip_coord(rb.x, a.inv_wx, a.nbx);
+                    const int b1 = live1 ? strip_coord(rb.z, a.inv_wx, a.nbx) : b0;
+                    const bool edge = (row == 0) | (row == a.nrows - 1) | (b0 < CL_K) | (b1 > a.nbx - 1 - CL_K);
+                    if (edge) {
+                        flags |= PR_EDGE;
+                    } else if (!direct) {
+                        unsigned m[6];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const int s = cs[(row + k - 1) * a.nbx + b0 - CL_K];
+                            const int e = cs[(row + k - 1) * a.nbx + b1 + CL_K + 1];
+                            m[2 * k]     = (unsigned)((s >> 1) - (ws[k] >> 1));
+                            m[2 * k + 1] = (unsigned)(((e + 1) >> 1) - (ws[k] >> 1));
+                        }
+                        w.x = m[0] | m[1] << 8 | m[2] << 16 | m[3] << 24;
+                        w.y = m[4] | m[5] << 8;
+                    }
+                }
+                w.y |= flags << 16;
+                a.pranges[p] = w;
+            }
+        }
+    }
+    CL_BARRIER();
+    CL_PROF(7);
 }
 
 // ---- packed pair evaluation ------------------------------------------------------------------------
@@ -369,7 +447,7 @@ __device__ __forceinline__ void row_range(const PairConsts& pc, const PairConsts
                                           const float2* __restrict__ X2, const float2* __restrict__ Y2,
                                           int m0, int m1, int pself, float2 nxi, float2 nyi, float2 nxs,
                                           float2 nys, PairAcc& acc) {
-#pragma unroll 2
+#pragma unroll CL_UNROLL
     for (int m = m0; m < m1; ++m) {
         const float2 xj = X2[m], yj = Y2[m];
         const bool k = (m != pself);
@@ -490,23 +568,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // order generic-proxy accesses (the previous step's st.global, made visible by the grid barrier)
 // against the async proxy (the bulk copies that read them)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CL_CONSUMERS) : "memory"); }
-
-// sum over the consumer threads (fixed shuffle tree + fixed warp order); result valid in thread 0
-__device__ __forceinline__ float consumer_sum(float v, float* sred /* CL_CONSUMERS/32 */) {
-    v = warp_sum(v);
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    consumer_sync();
-    if (l == 0) sred[w] = v;
-    consumer_sync();
-    float t = 0.0f;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < CL_CONSUMERS / 32; ++k) t += sred[k];
-    }
-    return t;
-}
-
 // sum of n floats in fixed order by the whole CTA, in double; result valid in every thread
 __device__ __forceinline__ double block_sum_array(const float* p, int n, double* sdbl /* CL_THREADS/32 */) {
     double t = 0.0;
@@ -521,83 +582,52 @@ __device__ __forceinline__ double block_sum_array(const float* p, int n, double*
     return tot;
 }
 
-// ---- producer: one chunk ahead of the consumers -----------------------------------------------------
-__device__ __forceinline__ void produce_step(const CellsArgs& a, Ctx& ctx, Stage* stages, StageMeta* meta,
-                                             unsigned long long* full, unsigned long long* empty, int par) {
+// ---- lane 0: issue the bulk copies of one unit into a stage of the warp's ring ---------------------
+struct PlanRegs { int4 q0, q1; };
+__device__ __forceinline__ PlanRegs load_plan(const CellsArgs& a, int u) {
+    const int4* __restrict__ pg = reinterpret_cast<const int4*>(a.plans + u);
+    PlanRegs q;
+    q.q0 = pg[0]; q.q1 = pg[1];
+    return q;
+}
+__device__ __forceinline__ void issue_unit(const CellsArgs& a, const Ctx& ctx, const PlanRegs& q, Stage& st,
+                                           unsigned long long* full) {
+    int4* ps = reinterpret_cast<int4*>(&st.plan);
+    ps[0] = q.q0; ps[1] = q.q1;
+    if (q.q0.w) return;                                  // direct unit: nothing staged
     const float* __restrict__ X = a.X[ctx.pr];
     const float* __restrict__ Y = a.Y[ctx.pr];
-    const float2* __restrict__ V = a.V[ctx.pv];
-    const int* __restrict__ og = a.orig[ctx.pv];
-    const int* __restrict__ cs = a.cell_start;
-    fence_proxy_async();
-    for (;;) {
-        // plan the next chunk (dependent index look-ups, ~4 L2 round trips) BEFORE waiting for a free
-        // stage: the look-ups overlap the consumers' work on the chunks in flight
-        const int c = atomicAdd(&a.sched[par], 1);
-        const bool last = (c >= ctx.nchunks);
-        int row = 0, slot0 = 0, n = 0, nent = 0;
-        int ws[3] = {0, 0, 0}, we[3] = {0, 0, 0}, cb[3] = {0, 0, 0}, nc[3] = {0, 0, 0};
-        bool direct = false;
-        if (!last) {
-            const int2 tab = a.chunk_tab[c];
-            row = tab.x; slot0 = tab.y;
-            const int rend = cs[(row + 1) * a.nbx];                    // next row's first slot (even)
-            n = min(CL_CH, rend - slot0);
-            const int bf = strip_coord(a.Rb[slot0].x, a.inv_wx, a.nbx);
-            const int bl = strip_coord(a.Rb[slot0 + n - 1].x, a.inv_wx, a.nbx);   // a pad clamps to the last bin
-            const int lo = max(bf - CL_K, 0), hi = min(bl + CL_K, a.nbx - 1);
-            nent = hi - lo + 2;                                        // cell_start entries lo .. hi+1
+    const int ws[3] = {q.q1.x, q.q1.y, q.q1.z};
+    const int nw[3] = {q.q1.w & 0xffff, (int)((unsigned)q.q1.w >> 16), (int)((unsigned)q.q0.z >> 16)};
+    const int slot0 = q.q0.y;
+    unsigned bytes = 32u * 8u;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                int rr = row + k - 1;
-                rr += (rr < 0) ? a.nrows : 0;
-                rr -= (rr >= a.nrows) ? a.nrows : 0;
-                const int c0 = rr * a.nbx + lo;
-                cb[k] = c0 & ~3;
-                nc[k] = ((c0 + nent + 3) & ~3) - cb[k];
-                ws[k] = cs[c0] & ~3;
-                we[k] = (cs[c0 + nent - 1] + 3) & ~3;
-                direct |= (we[k] - ws[k] > CL_WMAX) | (nc[k] > CL_CSMAX);
-            }
+    for (int k = 0; k < 3; ++k) bytes += (unsigned)nw[k] * 8u;
+    mbar_arrive_expect_tx(full, bytes);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (nw[k] > 0) {
+            bulk_g2s(st.x[k], X + ws[k], (unsigned)nw[k] * 4u, full);
+            bulk_g2s(st.y[k], Y + ws[k], (unsigned)nw[k] * 4u, full);
         }
-        const int s = (int)(ctx.it % CL_NST);
-        const unsigned ph = (ctx.it / CL_NST) & 1u;
-        ++ctx.it;
-        mbar_wait(&empty[s], ph ^ 1u);
-        StageMeta& m = meta[s];
-        if (last) { m.chunk = -1; mbar_arrive(&full[s]); break; }
-        const int own0 = slot0 & ~3, nown = ((slot0 + n + 3) & ~3) - own0;
-        m.chunk = c; m.row = row; m.slot0 = slot0; m.n = n; m.direct = direct ? 1 : 0; m.own0 = own0;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { m.ws[k] = ws[k]; m.cb[k] = cb[k]; }
-        if (direct) { mbar_arrive(&full[s]); continue; }
-        Stage& st = stages[s];
-        unsigned bytes = (unsigned)nown * (8u + 8u + 4u);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) bytes += (unsigned)(we[k] - ws[k]) * 8u + (unsigned)nc[k] * 4u;
-        mbar_arrive_expect_tx(&full[s], bytes);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            if (we[k] > ws[k]) {
-                bulk_g2s(st.x[k], X + ws[k], (unsigned)(we[k] - ws[k]) * 4u, &full[s]);
-                bulk_g2s(st.y[k], Y + ws[k], (unsigned)(we[k] - ws[k]) * 4u, &full[s]);
-            }
-            bulk_g2s(st.cs[k], cs + cb[k], (unsigned)nc[k] * 4u, &full[s]);
-        }
-        bulk_g2s(st.rb, a.Rb + own0, (unsigned)nown * 8u, &full[s]);
-        bulk_g2s(st.v, V + own0, (unsigned)nown * 8u, &full[s]);
-        bulk_g2s(st.og, og + own0, (unsigned)nown * 4u, &full[s]);
     }
+    bulk_g2s(st.pr, a.pranges + (slot0 >> 1), 32u * 8u, full);
 }
 
-// ---- consumers: forces + integrate of one chunk ----------------------------------------------------
+// dynamic schedule: lane 0 draws the next unit from a per-step counter (one atomic per unit, issued
+// two units ahead of its use); -1 = no more units
+__device__ __forceinline__ int next_unit(const CellsArgs& a, const Ctx& ctx, int par) {
+    const int u = atomicAdd(&a.sched[par], 1);
+    return (u < ctx.nunits) ? u : -1;
+}
+
+// ---- forces + integrate of one unit (one warp) ------------------------------------------------------
 template <bool PE, bool STAGED>
-__device__ __forceinline__ void chunk_compute(const CellsArgs& a, const Ctx& ctx, const StepFlags& fl,
-                                              const StageMeta& m, const StageMeta& ms, const Stage& st,
-                                              float& pe_thread, float& ke_thread, int& moved) {
-    // m: register copy of the stage header; ms: the same header in shared memory (fields indexed at
-    // run time are read from there, not from a local-memory copy)
-    const int t = threadIdx.x;
+__device__ __forceinline__ void unit_compute(const CellsArgs& a, const Ctx& ctx, const StepFlags& fl,
+                                             const Stage& st, float& pe_thread, float& ke_thread,
+                                             int& moved) {
+    const UnitPlan& m = st.plan;                       // (in shared memory)
+    const int t = threadIdx.x & 31;
     const PairConsts pc = a.pc;
     const PairConsts2 c2 = make_pair_consts2(pc);
     const float2* __restrict__ X2g = reinterpret_cast<const float2*>(a.X[ctx.pr]);
@@ -606,86 +636,74 @@ __device__ __forceinline__ void chunk_compute(const CellsArgs& a, const Ctx& ctx
     float2* Yn2 = reinterpret_cast<float2*>(a.Y[ctx.pr ^ 1]);
     float4* V4 = reinterpret_cast<float4*>(a.V[ctx.pv]);
     const int* __restrict__ csg = a.cell_start;
-    const int  p = (m.slot0 >> 1) + t;                 // global slot-pair index
-    const bool act = 2 * t < m.n;
+    const int  slot0 = m.slot0, nslots = m.n & 0xffff, r = m.row;
+    const int  p = (slot0 >> 1) + t;                   // global slot-pair index
+    const bool act = 2 * t < nslots;
     float2 xi = make_float2(CL_SENT, CL_SENT), yi = xi;
     float4 rb = make_float4(CL_SENT, CL_SENT, CL_SENT, CL_SENT);
     float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     int2 o = make_int2(-1, -1);
+    uint2 pr = make_uint2(0u, 0u);
     if (act) {
+        // build positions, velocities and original indices are only needed by the epilogue: plain
+        // coalesced loads, issued now, consumed after the pair loop
+        rb = reinterpret_cast<const float4*>(a.Rb)[p];
+        o = reinterpret_cast<const int2*>(a.orig[ctx.pv])[p];
+        if (a.rc.nsteps > 0) v = V4[p];
         if (STAGED) {
-            const int q = ((m.slot0 - m.own0) >> 1) + t;
-            rb = reinterpret_cast<const float4*>(st.rb)[q];
-            o  = reinterpret_cast<const int2*>(st.og)[q];
-            if (a.rc.nsteps > 0) v = reinterpret_cast<const float4*>(st.v)[q];
-            xi = reinterpret_cast<const float2*>(st.x[1])[p - (m.ws[1] >> 1)];
-            yi = reinterpret_cast<const float2*>(st.y[1])[p - (m.ws[1] >> 1)];
+            const int q = p - (m.ws[1] >> 1);
+            pr = st.pr[t];
+            xi = reinterpret_cast<const float2*>(st.x[1])[q];
+            yi = reinterpret_cast<const float2*>(st.y[1])[q];
         } else {
+            pr = a.pranges[p];
             xi = X2g[p]; yi = Y2g[p];
-            rb = reinterpret_cast<const float4*>(a.Rb)[p];
-            o  = reinterpret_cast<const int2*>(a.orig[ctx.pv])[p];
-            if (a.rc.nsteps > 0) v = V4[p];
         }
     }
-    const bool live0 = o.x >= 0, live1 = o.y >= 0;
-    const int r = m.row;
-    int b0 = CL_K, b1 = CL_K;
-    if (live0) {
-        b0 = strip_coord(rb.x, a.inv_wx, a.nbx);
-        b1 = live1 ? strip_coord(rb.z, a.inv_wx, a.nbx) : b0;
-    }
-    const bool yedge = (r == 0) | (r == a.nrows - 1);
-    const bool edge = live0 & (yedge | (b0 < CL_K) | (b1 > a.nbx - 1 - CL_K));
-    const bool wedge = __any_sync(0xffffffffu, edge);
+    const unsigned flags = pr.y >> 16;
+    const bool live0 = (flags & PR_LIVE0) != 0, live1 = (flags & PR_LIVE1) != 0;
+    const bool wedge = __any_sync(0xffffffffu, (flags & PR_EDGE) != 0);
     PairAcc acc;
     acc.axA = acc.ayA = acc.axB = acc.ayB = acc.peA = acc.peB = make_float2(0.0f, 0.0f);
     const float2 nxi = make_float2(-xi.x, -xi.y), nyi = make_float2(-yi.x, -yi.y);
     const float2 nxs = make_float2(-xi.y, -xi.x), nys = make_float2(-yi.y, -yi.x);
-    if (!wedge) {
+    if (STAGED && !wedge) {
+        // the common case: three precomputed ranges, straight out of the staged windows
         if (live0) {
+            const unsigned long long w = (unsigned long long)pr.x | ((unsigned long long)(pr.y & 0xffffu) << 32);
 #pragma unroll 1
             for (int k = 0; k < 3; ++k) {       // rows r-1, r, r+1: one contiguous range each
-                const int cl = (r + k - 1) * a.nbx + b0 - CL_K, ch = (r + k - 1) * a.nbx + b1 + CL_K + 1;
-                const int pself = (k == 1) ? p : -1;
-                if (STAGED) {
-                    const int cb = ms.cb[k], w2 = ms.ws[k] >> 1;
-                    const int s = st.cs[k][cl - cb], e = st.cs[k][ch - cb];
-                    const float2* xw = reinterpret_cast<const float2*>(st.x[k]) - w2;
-                    const float2* yw = reinterpret_cast<const float2*>(st.y[k]) - w2;
-                    row_range<PE>(pc, c2, xw, yw, s >> 1, (e + 1) >> 1, pself, nxi, nyi, nxs, nys, acc);
-                } else {
-                    const int s = csg[cl], e = csg[ch];
-                    row_range<PE>(pc, c2, X2g, Y2g, s >> 1, (e + 1) >> 1, pself, nxi, nyi, nxs, nys, acc);
-                }
+                const int m0 = (int)((w >> (16 * k)) & 0xffu), m1 = (int)((w >> (16 * k + 8)) & 0xffu);
+                const int pself = (k == 1) ? p - (m.ws[1] >> 1) : -1;
+                row_range<PE>(pc, c2, reinterpret_cast<const float2*>(st.x[k]),
+                              reinterpret_cast<const float2*>(st.y[k]), m0, m1, pself, nxi, nyi, nxs, nys, acc);
             }
         }
     } else if (live0) {
-        // bins [b0-K, b1+K] of rows r-1, r, r+1 with periodic wrap of both indices: one piece plus up
-        // to two wrapped pieces per row (the whole row once if the union would overlap itself).
-        // The unwrapped piece lies inside the staged window; wrapped pieces are read from global.
-        int lo = b0 - CL_K, hi = b1 + CL_K;
-        const bool whole = (hi - lo + 1 > a.nbx);
-        if (whole) { lo = 0; hi = a.nbx - 1; }
+        // edge warps and oversized units: ranges from the global cell index, positions from global
+        const int b0 = strip_coord(rb.x, a.inv_wx, a.nbx);
+        const int b1 = live1 ? strip_coord(rb.z, a.inv_wx, a.nbx) : b0;
+        if (!wedge) {
 #pragma unroll 1
-        for (int k = 0; k < 3; ++k) {
-            int rr = r + k - 1;
-            rr += (rr < 0) ? a.nrows : 0;
-            rr -= (rr >= a.nrows) ? a.nrows : 0;
-            const int* __restrict__ csr = csg + rr * a.nbx;
-            {
-                const int bl = max(lo, 0), bh = min(hi, a.nbx - 1);
-                if (STAGED && !whole) {
-                    const int cb = ms.cb[k], w2 = ms.ws[k] >> 1;
-                    const int s = st.cs[k][rr * a.nbx + bl - cb], e = st.cs[k][rr * a.nbx + bh + 1 - cb];
-                    const float2* xw = reinterpret_cast<const float2*>(st.x[k]) - w2;
-                    const float2* yw = reinterpret_cast<const float2*>(st.y[k]) - w2;
-                    edge_range<PE>(pc, c2, xw, yw, s, e, p, nxi, nyi, nxs, nys, acc);
-                } else {
-                    edge_range<PE>(pc, c2, X2g, Y2g, csr[bl], csr[bh + 1], p, nxi, nyi, nxs, nys, acc);
-                }
+            for (int k = 0; k < 3; ++k) {
+                const int s = csg[(r + k - 1) * a.nbx + b0 - CL_K], e = csg[(r + k - 1) * a.nbx + b1 + CL_K + 1];
+                row_range<PE>(pc, c2, X2g, Y2g, s >> 1, (e + 1) >> 1, (k == 1) ? p : -1, nxi, nyi, nxs, nys, acc);
             }
-            if (lo < 0)      edge_range<PE>(pc, c2, X2g, Y2g, csr[lo + a.nbx], csr[a.nbx], p, nxi, nyi, nxs, nys, acc);
-            if (hi >= a.nbx) edge_range<PE>(pc, c2, X2g, Y2g, csr[0], csr[hi - a.nbx + 1], p, nxi, nyi, nxs, nys, acc);
+        } else {
+            // bins [b0-K, b1+K] of rows r-1, r, r+1 with periodic wrap of both indices: one piece plus
+            // up to two wrapped pieces per row (the whole row once if the union would overlap itself)
+            int lo = b0 - CL_K, hi = b1 + CL_K;
+            if (hi - lo + 1 > a.nbx) { lo = 0; hi = a.nbx - 1; }
+#pragma unroll 1
+            for (int k = 0; k < 3; ++k) {
+                int rr = r + k - 1;
+                rr += (rr < 0) ? a.nrows : 0;
+                rr -= (rr >= a.nrows) ? a.nrows : 0;
+                const int* __restrict__ csr = csg + rr * a.nbx;
+                edge_range<PE>(pc, c2, X2g, Y2g, csr[max(lo, 0)], csr[min(hi, a.nbx - 1) + 1], p, nxi, nyi, nxs, nys, acc);
+                if (lo < 0)      edge_range<PE>(pc, c2, X2g, Y2g, csr[lo + a.nbx], csr[a.nbx], p, nxi, nyi, nxs, nys, acc);
+                if (hi >= a.nbx) edge_range<PE>(pc, c2, X2g, Y2g, csr[0], csr[hi - a.nbx + 1], p, nxi, nyi, nxs, nys, acc);
+            }
         }
     }
     // accumulators hold -F:  i0 <- straight.x + swapped.y,  i1 <- straight.y + swapped.x
@@ -693,6 +711,9 @@ __device__ __forceinline__ void chunk_compute(const CellsArgs& a, const Ctx& ctx
     const float F1x = -(acc.axA.y + acc.axB.x), F1y = -(acc.ayA.y + acc.ayB.x);
     if (PE) pe_thread += (acc.peA.x + acc.peB.y) + (acc.peA.y + acc.peB.x);
     if (!act) return;
+    // the epilogue operands were requested before the pair loop; this keeps the compiler from
+    // hoisting their first use (e.g. the sign extension of an index) up to the load
+    asm volatile("" : "+r"(o.x), "+r"(o.y), "+f"(rb.x), "+f"(v.x) :: "memory");
     float2 v0 = make_float2(v.x, v.y), v1 = make_float2(v.z, v.w);
     float2 xn = xi, yn = yi;
     if (live0) moved |= finish_particle(a, fl, 2 * p, o.x, xi.x, yi.x, F0x, F0y, v0, make_float2(rb.x, rb.y), xn.x, yn.x, ke_thread);
@@ -703,67 +724,95 @@ __device__ __forceinline__ void chunk_compute(const CellsArgs& a, const Ctx& ctx
     }
 }
 
+// ---- one step's pass of one warp --------------------------------------------------------------------
+// Software pipeline, three units deep, driven by lane 0: while unit u is evaluated, the bulk copies of
+// the next unit are in flight, the copy plan of the one after is being loaded, and the index of the
+// one after that is being drawn from the step's counter.  Which warp evaluates which unit does not
+// affect any result (energies are per-unit partials).
 template <bool PE>
-__device__ __forceinline__ void consume_step(const CellsArgs& a, Ctx& ctx, const StepFlags& fl,
-                                             const Stage* stages, const StageMeta* meta,
-                                             unsigned long long* full, unsigned long long* empty,
-                                             float* sred, int par, bool want_ke, int& moved) {
-    for (;;) {
-        const int s = (int)(ctx.it % CL_NST);
-        const unsigned ph = (ctx.it / CL_NST) & 1u;
-        ++ctx.it;
-        mbar_wait(&full[s], ph);
-        const StageMeta m = meta[s];
-        if (m.chunk >= 0) {
-            float pe_thread = 0.0f, ke_thread = 0.0f;
-            if (m.direct) chunk_compute<true, false>(a, ctx, fl, m, meta[s], stages[s], pe_thread, ke_thread, moved);
-            else          chunk_compute<PE, true >(a, ctx, fl, m, meta[s], stages[s], pe_thread, ke_thread, moved);
-            // per-chunk energy partials, reduced in chunk order after the barrier: independent of
-            // which CTA ran the chunk
-            if (PE) {
-                const float tsum = consumer_sum(pe_thread, sred);
-                if (threadIdx.x == 0) __stcg(&a.pe_part[par * a.maxchunks + m.chunk], tsum);
-            }
-            if (want_ke) {
-                const float tsum = consumer_sum(ke_thread, sred);
-                if (threadIdx.x == 0) __stcg(&a.ke_part[par * a.maxchunks + m.chunk], tsum);
-            }
+__device__ __forceinline__ void warp_force_pass(const CellsArgs& a, Ctx& ctx, const StepFlags& fl,
+                                                Stage* ring /* this warp's CL_NST stages */,
+                                                unsigned long long* full /* this warp's CL_NST barriers */,
+                                                int par, bool want_ke, int& moved) {
+    const int lane = threadIdx.x & 31;
+    int u = -1, un = -1, unn = -1, unnn = -1;            // meaningful in lane 0 only
+    PlanRegs qn;
+    qn.q0 = qn.q1 = make_int4(0, 0, 0, 0);
+    if (lane == 0) {
+        fence_proxy_async();
+        u = next_unit(a, ctx, par);
+        un = (u >= 0) ? next_unit(a, ctx, par) : -1;
+        unn = (un >= 0) ? next_unit(a, ctx, par) : -1;
+        if (u >= 0) {
+            const PlanRegs q = load_plan(a, u);
+            issue_unit(a, ctx, q, ring[ctx.uses % CL_NST], &full[ctx.uses % CL_NST]);
         }
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);
-        if (m.chunk < 0) break;
+        if (un >= 0) qn = load_plan(a, un);
+    }
+    for (;;) {
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u < 0) break;
+        const int s = (int)(ctx.uses % CL_NST);
+        ++ctx.uses;
+        __syncwarp();                                    // every lane is done with the other stage
+        if (lane == 0) {
+            if (unn >= 0) unnn = next_unit(a, ctx, par); // consumed two units from now
+            if (un >= 0) issue_unit(a, ctx, qn, ring[s ^ 1], &full[s ^ 1]);
+            if (unn >= 0) qn = load_plan(a, unn);        // consumed one unit from now
+        }
+        __syncwarp();                                    // plan of unit u (written by lane 0) is visible
+        const Stage& st = ring[s];
+        const bool direct = st.plan.direct != 0;
+        float pe_thread = 0.0f, ke_thread = 0.0f;
+        if (direct) {
+            unit_compute<true, false>(a, ctx, fl, st, pe_thread, ke_thread, moved);
+        } else {
+            mbar_wait(&full[s], (ctx.phase >> s) & 1u);
+            ctx.phase ^= 1u << s;
+            unit_compute<PE, true>(a, ctx, fl, st, pe_thread, ke_thread, moved);
+        }
+        // per-unit energy partials (fixed shuffle tree), reduced in unit order after the barrier
+        if (PE) {
+            const float tsum = warp_sum(pe_thread);
+            if (lane == 0) __stcg(&a.pe_part[par * a.maxunits + u], tsum);
+        }
+        if (want_ke) {
+            const float tsum = warp_sum(ke_thread);
+            if (lane == 0) __stcg(&a.ke_part[par * a.maxunits + u], tsum);
+        }
+        u = un; un = unn; unn = unnn; unnn = -1;
     }
 }
 
 extern __shared__ __align__(128) unsigned char cells_smem[];
 
-__global__ void __launch_bounds__(CL_THREADS, 2)
+__global__ void __launch_bounds__(CL_THREADS, LJMD_CELLS_MINBLOCKS)
 cells_persistent_kernel(const CellsArgs a) {
     __shared__ int    sscan[CL_THREADS / 32 + 1];
-    __shared__ float  sred[CL_THREADS / 32];
     __shared__ double sdbl[CL_THREADS / 32];
     __shared__ float  s_lambda;
     __shared__ long long s_pt[12];
-    __shared__ __align__(8) unsigned long long s_full[CL_NST], s_empty[CL_NST];
-    __shared__ StageMeta s_meta[CL_NST];
+    __shared__ __align__(8) unsigned long long s_full[CL_WARPS][CL_NST];
     Stage* stages = reinterpret_cast<Stage*>(cells_smem);
     const int tid = threadIdx.x, gtid = blockIdx.x * CL_THREADS + tid, gsz = a.G * CL_THREADS;
-    const bool producer = tid >= CL_CONSUMERS;
+    const int warp = tid >> 5;
     const RunCtl rc = a.rc;
     Ctx ctx;
     ctx.epoch = 0;
-    ctx.it = 0;
+    ctx.uses = 0;
+    ctx.phase = 0;
     ctx.pt = a.prof ? s_pt : nullptr;
     if (tid == 0) {
         if (ctx.pt) { for (int k = 0; k < 11; ++k) s_pt[k] = 0; s_pt[11] = clock64(); }
-        for (int k = 0; k < CL_NST; ++k) { mbar_init(&s_full[k], 1); mbar_init(&s_empty[k], CL_CONSUMERS / 32); }
+        for (int w = 0; w < CL_WARPS; ++w)
+            for (int k = 0; k < CL_NST; ++k) mbar_init(&s_full[w][k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     ctx.pr = a.state[ST_PR];
     ctx.pv = a.state[ST_PV];
     ctx.ntot = a.state[ST_NTOT];
-    ctx.nchunks = a.state[ST_NCHUNKS];
+    ctx.nunits = a.state[ST_NUNITS];
 
     if (a.s_begin < 0) {
         // load the caller's state (original order, no pads) and sort it
@@ -813,20 +862,18 @@ cells_persistent_kernel(const CellsArgs a) {
         if (s > a.s_begin || a.s_begin >= 0) {
             if (__ldcg(a.state + ST_FLAG) == (int)(s + 1)) cells_rebuild(a, ctx, sscan);
         }
-        // the other parity's chunk counter is idle during this step: clear it for the next one
+        // the other parity's unit counter is idle during this step: clear it for the next one
         if (gtid == 0) __stcg(&a.sched[par ^ 1], 0);
         int moved = 0;
-        if (producer) {
-            if (tid == CL_CONSUMERS) produce_step(a, ctx, stages, s_meta, s_full, s_empty, par);
-            ctx.it = __shfl_sync(0xffffffffu, ctx.it, 0);
-        } else {
+        {
             const bool want_ke = fl.want_e || fl.thermo;
-            if (want_pe) consume_step<true >(a, ctx, fl, stages, s_meta, s_full, s_empty, sred, par, want_ke, moved);
-            else         consume_step<false>(a, ctx, fl, stages, s_meta, s_full, s_empty, sred, par, want_ke, moved);
+            Stage* ring = stages + warp * CL_NST;
+            if (want_pe) warp_force_pass<true >(a, ctx, fl, ring, s_full[warp], par, want_ke, moved);
+            else         warp_force_pass<false>(a, ctx, fl, ring, s_full[warp], par, want_ke, moved);
         }
         if (fl.thermo) {
             CL_BARRIER();
-            const double ke2 = block_sum_array(a.ke_part + par * a.maxchunks, ctx.nchunks, sdbl);
+            const double ke2 = block_sum_array(a.ke_part + par * a.maxunits, ctx.nunits, sdbl);
             if (tid == 0) s_lambda = sqrtf(rc.thermo_kT / ((float)(0.5 * ke2) / (float)a.N));
             __syncthreads();
             const float lam = s_lambda;
@@ -868,9 +915,9 @@ cells_persistent_kernel(const CellsArgs a) {
         CL_PROF(1);
 
         if (blockIdx.x == 0 && want_pe) {
-            const double pe2 = block_sum_array(a.pe_part + par * a.maxchunks, ctx.nchunks, sdbl);
+            const double pe2 = block_sum_array(a.pe_part + par * a.maxunits, ctx.nunits, sdbl);
             double ke2 = 0.0;
-            if (fl.want_e) ke2 = block_sum_array(a.ke_part + par * a.maxchunks, ctx.nchunks, sdbl);
+            if (fl.want_e) ke2 = block_sum_array(a.ke_part + par * a.maxunits, ctx.nunits, sdbl);
             if (tid == 0) {
                 if (fl.want_e) {
                     float* o = rc.ke_pe + 2 * (s / rc.energy_every);
@@ -911,8 +958,10 @@ struct Cells {
     int *orig[2] = {nullptr, nullptr};
     int *key = nullptr, *rank = nullptr, *tmp = nullptr, *cell_count = nullptr, *cell_start = nullptr,
         *row_tot = nullptr, *sched = nullptr;
-    int2* chunk_tab = nullptr;
-    int maxchunks = 0;
+    int2* unit_tab = nullptr;
+    UnitPlan* plans = nullptr;
+    uint2* pranges = nullptr;
+    int maxunits = 0;
     size_t smem = 0;
     float *pe_part = nullptr, *ke_part = nullptr;
     int* state = nullptr;
@@ -943,17 +992,17 @@ int cells_create(ljmd_handle* h) {
     cl->wx = h->p.box / (float)cl->nbx;
     cl->inv_hy = (float)cl->nrows / h->p.box;
     cl->inv_wx = (float)cl->nbx / h->p.box;
-    cl->Nalloc = (int)(((N + cl->nrows + 63) / 64) * 64 + 64);
+    cl->Nalloc = (int)(((N + 3 * (long long)cl->nrows + 63) / 64) * 64 + 64);
 
-    cl->maxchunks = (int)(N / CL_CH + cl->nrows + 2);
-    cl->smem = sizeof(Stage) * CL_NST;
+    cl->maxunits = (int)(N / CL_UNIT + cl->nrows + 2);
+    cl->smem = sizeof(Stage) * CL_NST * CL_WARPS;
     LJ_CUDA(cudaFuncSetAttribute(cells_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl->smem));
     int per_sm = 0;
     LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cells_persistent_kernel, CL_THREADS, cl->smem));
     if (per_sm < 1) { set_error("cell-list kernel does not fit on an SM"); return LJMD_E_STATE; }
     if (const char* e = getenv("LJMD_CELLS_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));
     long long g = (long long)per_sm * h->num_sms;
-    g = std::min<long long>(g, std::max<long long>(1, (N + CL_CH - 1) / CL_CH));
+    g = std::min<long long>(g, std::max<long long>(1, (N + CL_UNIT * CL_WARPS - 1) / (CL_UNIT * CL_WARPS)));
     cl->G = (int)g;
 
     const size_t na = (size_t)cl->Nalloc;
@@ -973,10 +1022,13 @@ int cells_create(ljmd_handle* h) {
     LJ_CUDA(cudaMalloc(&cl->cell_start, sizeof(int) * ((size_t)cl->ncells + 1 + 8)));   // + bulk-copy round-up
     LJ_CUDA(cudaMemset(cl->cell_start, 0, sizeof(int) * ((size_t)cl->ncells + 1 + 8)));
     LJ_CUDA(cudaMalloc(&cl->row_tot, sizeof(int) * (size_t)cl->nrows));
-    LJ_CUDA(cudaMalloc(&cl->chunk_tab, sizeof(int2) * (size_t)cl->maxchunks));
+    LJ_CUDA(cudaMalloc(&cl->unit_tab, sizeof(int2) * (size_t)cl->maxunits));
+    LJ_CUDA(cudaMalloc(&cl->plans, sizeof(UnitPlan) * (size_t)cl->maxunits));
     LJ_CUDA(cudaMalloc(&cl->sched, sizeof(int) * 2));
-    LJ_CUDA(cudaMalloc(&cl->pe_part, sizeof(float) * 2 * cl->maxchunks));
-    LJ_CUDA(cudaMalloc(&cl->ke_part, sizeof(float) * 2 * cl->maxchunks));
+    LJ_CUDA(cudaMalloc(&cl->pranges, sizeof(uint2) * (na / 2 + 64)));
+    LJ_CUDA(cudaMemset(cl->pranges, 0, sizeof(uint2) * (na / 2 + 64)));
+    LJ_CUDA(cudaMalloc(&cl->pe_part, sizeof(float) * 2 * cl->maxunits));
+    LJ_CUDA(cudaMalloc(&cl->ke_part, sizeof(float) * 2 * cl->maxunits));
     LJ_CUDA(cudaMalloc(&cl->state, sizeof(int) * ST_WORDS));
     LJ_CUDA(cudaMemset(cl->state, 0, sizeof(int) * ST_WORDS));
     LJ_CUDA(cudaMalloc(&cl->bar, sizeof(unsigned)));
@@ -990,7 +1042,7 @@ void cells_destroy(ljmd_handle* h) {
     for (int k = 0; k < 2; ++k) { cudaFree(cl->X[k]); cudaFree(cl->Y[k]); cudaFree(cl->V[k]); cudaFree(cl->orig[k]); }
     cudaFree(cl->Rb); cudaFree(cl->Fs); cudaFree(cl->key); cudaFree(cl->rank); cudaFree(cl->tmp);
     cudaFree(cl->cell_count); cudaFree(cl->cell_start); cudaFree(cl->row_tot);
-    cudaFree(cl->chunk_tab); cudaFree(cl->sched);
+    cudaFree(cl->unit_tab); cudaFree(cl->plans); cudaFree(cl->pranges); cudaFree(cl->sched);
     cudaFree(cl->pe_part); cudaFree(cl->ke_part);
     cudaFree(cl->state); cudaFree(cl->bar); cudaFree(cl->prof);
     delete cl;
@@ -1009,7 +1061,8 @@ static void fill_args(ljmd_handle* h, CellsArgs& a) {
     a.Rb = cl->Rb; a.Fs = cl->Fs;
     a.key = cl->key; a.rank = cl->rank; a.tmp = cl->tmp;
     a.cell_count = cl->cell_count; a.cell_start = cl->cell_start; a.row_tot = cl->row_tot;
-    a.chunk_tab = cl->chunk_tab; a.sched = cl->sched; a.maxchunks = cl->maxchunks;
+    a.sched = cl->sched;
+    a.unit_tab = cl->unit_tab; a.plans = cl->plans; a.pranges = cl->pranges; a.maxunits = cl->maxunits;
     a.pe_part = cl->pe_part; a.ke_part = cl->ke_part;
     a.state = cl->state; a.bar = cl->bar; a.prof = cl->prof;
 }
@@ -1059,9 +1112,9 @@ int cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_
         LJ_CUDA(cudaStreamSynchronize(st));
         std::vector<long long> pv(12 * cl->G);
         LJ_CUDA(cudaMemcpy(pv.data(), cl->prof, sizeof(long long) * pv.size(), cudaMemcpyDeviceToHost));
-        const char* nm[7] = {"force+integrate", "step barrier", "B1 bin+hist", "B2 row totals",
-                             "B3 scan", "B4 scatter", "B5 order+gather"};
-        for (int k = 0; k < 7; ++k) {
+        const char* nm[8] = {"force+integrate", "step barrier", "B1 bin+hist", "B2 row totals",
+                             "B3 scan", "B4 scatter", "B5 order+gather", "B6 copy plans"};
+        for (int k = 0; k < 8; ++k) {
             double mean = 0, mx = 0;
             for (int c = 0; c < cl->G; ++c) { mean += pv[c * 12 + k]; mx = std::max<double>(mx, (double)pv[c * 12 + k]); }
             fprintf(stderr, "[ljmd cells prof] %-16s mean %12.0f  max %12.0f clocks (launch total)\n", nm[k], mean / cl->G, mx);
