@@ -1,4 +1,4 @@
-// cells.cu — sorted strip-cell path for large N (BASELINE configs 4-5).
+// cells.cu — sorted strip-cell / bitmask-Verlet-list path for large N (BASELINE configs 4-5).
 //
 // Not in the reference (it only has the dense O(N^2) form, MD:51): the pair arithmetic is the
 // same as the all-pairs path (subtract, exact min-image, unfused r2, r2 < rc^2), so on identical
@@ -6,36 +6,34 @@
 //
 // Geometry.  The box is cut into `nrows` horizontal rows of height >= rc + skin and every row into
 // `nbx` narrow bins of width >= (rc + skin) / K  (K = 4).  Cells (row, bin) are numbered row-major
-// and the particle state is kept SORTED by cell.  Everything within rc + skin of a particle of cell
-// (r, b) lies in bins [b-K, b+K] of rows r-1, r, r+1, i.e. in THREE CONTIGUOUS RANGES of the sorted
-// arrays: no neighbour list is stored, built or gathered; the per-step pass streams contiguous,
-// vectorised position loads (9 narrow bins per row = 42 candidates/particle at rho 0.8, against 57
-// for square 3x3 cells) and the rebuild is only a counting sort.
+// and the particle state is kept SORTED by cell ("slots").  Everything within rc + skin of a particle
+// of cell (r, b) lies in bins [b-K, b+K] of rows r-1, r, r+1, i.e. in THREE CONTIGUOUS SLOT RANGES
+// (42 candidates at rho 0.8, against 57 for square 3x3 cells).
 //
-// Data layout in HBM (all in cell-sorted "slot" order; every row starts on a multiple of 4 slots and
-// is padded with sentinel slots, so slots pair up as aligned float2 and bulk copies stay 16-byte aligned):
-//   X[2], Y[2]  float   positions, structure-of-arrays, ping-pong by step (the buffer being read is
-//                        never written in a step).  One 64-bit load = the x of two adjacent slots
-//                        = one operand of the packed FP32x2 pipe.
-//   V[2]        float2  velocities (buffers swap at a rebuild)
-//   orig[2]     int32   original particle index of each slot (-1 = pad)
-//   Rb          float2  positions at the last rebuild (max-displacement test against skin/2; also
-//                        gives the slot's cell, hence its three candidate ranges)
-//   cell_start  int32   prefix-sum cell index over nrows*nbx cells (+1)
+// Neighbour list.  Because the candidates are contiguous, a particle's Verlet list is a few
+// (first slot, 32-bit mask) entries — normally one per stencil row, 24 bytes per particle instead of
+// 4 bytes per neighbour — built at a rebuild from the same fp32 r2 as the force loop.  The per-step
+// pass walks the set bits two at a time: two neighbours of one particle fill the two lanes of the
+// packed FP32x2 instructions.
 //
-// One PERSISTENT cooperative kernel runs a whole ljmd_run().  Per step ONE pass over the state and
-// one grid barrier.  A row is cut into units of 64 slots = one warp (each thread owns two adjacent
-// slots).  Every warp is its own producer and consumer: before it evaluates unit u it issues the TMA
-// bulk copies (cp.async.bulk, mbarrier complete_tx) of everything unit u+1 needs — the x / y windows
-// of rows r-1, r, r+1, the matching slices of the cell index and the unit's own Rb — into its private
-// 2-stage shared-memory ring, from a per-unit copy plan that the rebuild precomputes.  The pair loop
-// reads shared memory only (no load in it can miss), then velocity-Verlet + energies + displacement
-// test and the new state is written: each particle's state is read once and written once per step.
-// Warps never wait for each other inside a step.  Energies are per-unit partials reduced in unit
-// order (deterministic).
-// The rebuild (bin + histogram with rank capture -> row-structured prefix sum -> scatter ->
-// deterministic in-cell order by original index + gather -> copy plans) runs inside the same kernel
-// under a grid-uniform condition: no host round trip (MD:82,103).
+// Data layout in HBM (all in slot order, permuted only at a rebuild):
+//   R[2]     float2  positions, ping-pong by step (the buffer being read is never written in a step)
+//   V[2]     float2  velocities (buffers swap at a rebuild)
+//   orig[2]  int32   original particle index of each slot
+//   Rb       float2  positions at the last rebuild (max-displacement test against skin/2)
+//   meta     uint32  number of list entries | edge flag << 8 (particle needs the minimum image)
+//   ent      uint2   list entries, ELL layout ent[k * Nalloc + i] = (first slot, mask)
+//   wplan    int4 x2 per warp of 32 slots: the three contiguous slot windows that hold every
+//                    neighbour of the warp's particles.  The per-step pass copies them to shared
+//                    memory with coalesced loads, so the gathers of the pair loop are LDS, not
+//                    scattered global loads; entries of such a warp are window-relative.
+//   cell_start int32 prefix-sum cell index over nrows*nbx cells (+1)
+//
+// One PERSISTENT cooperative kernel runs a whole ljmd_run(): per step ONE pass over the state
+// (thread = particle: list forces + velocity-Verlet + energies + displacement test; state read once,
+// written once) and one grid barrier.  The rebuild (bin + histogram with rank capture -> row-wise
+// prefix sum -> scatter -> deterministic in-cell order by original index + gather -> list build)
+// runs inside the same kernel under a grid-uniform condition: no host round trip (MD:82,103).
 #include "ljmd_device.cuh"
 
 #include <algorithm>
@@ -45,72 +43,31 @@ namespace ljmd {
 
 namespace {
 
-#ifndef LJMD_CELLS_UNROLL
-#define LJMD_CELLS_UNROLL 2
-#endif
-#ifndef LJMD_CELLS_MINBLOCKS
-#define LJMD_CELLS_MINBLOCKS 2
-#endif
-constexpr int   CL_UNROLL  = LJMD_CELLS_UNROLL;
-constexpr int   CL_THREADS = 256;                  // 8 warps, each with a private TMA ring
-constexpr int   CL_WARPS   = CL_THREADS / 32;
-constexpr int   CL_UNIT    = 64;                   // slots per unit (one warp, two slots per thread)
-constexpr int   CL_NST     = 2;                    // stages of a warp's ring
-constexpr int   CL_WMAX    = 160;                  // staged window capacity per row (slots): a lattice
-                                                   // row of 3 lattice lines beside one of 2 needs 1.5 units
-constexpr int   CL_K       = 4;        // bins per (rc + skin)
-constexpr int   CL_ORDER_MAX = 64;     // cells denser than this keep arrival order (see B5)
-// Pad slots sit far outside any box, each at its OWN place (pad_x): two pads must never coincide,
-// because a zero r2 would poison its partner in the shared-reciprocal evaluation (0 * inf).
-// Squares and products of two squared distances stay far inside the fp32 range.
-constexpr float CL_SENT    = 1.0e8f;
+constexpr int CL_THREADS   = 512;
+constexpr int CL_K         = 4;     // bins per (rc + skin)
+constexpr int CL_E         = 8;     // list entries per particle (3 when every range fits 32 slots)
+constexpr int CL_WIN       = 96;    // staged window capacity per stencil row and warp (slots)
+constexpr int CL_WARPS     = CL_THREADS / 32;
+constexpr int CL_ORDER_MAX = 64;    // cells denser than this keep arrival order (see B5)
 
-#ifndef LJMD_CELLS_RCP_PRODUCT
-#define LJMD_CELLS_RCP_PRODUCT 0       // 1: one MUFU.RCP per TWO pairs (1/(a*b) trick), see eval_set
-#endif
-
-enum { ST_PR = 0, ST_PV = 1, ST_REBUILDS = 2, ST_ERR = 3, ST_FLAG = 4, ST_NTOT = 5, ST_NUNITS = 6,
-       ST_WORDS = 8 };
-enum { CERR_BARRIER = 1 };
-
-// copy plan of one unit, precomputed by the rebuild (32 bytes)
-struct __align__(16) UnitPlan {
-    int row, slot0, n, direct;     // row, first slot, number of slots (even); direct = 1: windows too
-                                   // large for a stage, the unit reads global memory
-    int ws[3];                     // first staged slot of each window   (multiple of 4)
-    int nw01;                      // staged slots of windows 0 and 1    (multiples of 4, 16 bits each)
-    // (the size of window 2 travels in the upper half of `n`)
-};
-// candidate ranges of one thread (= two adjacent slots), precomputed by the rebuild: for each stencil
-// row the slot-PAIR range [m0, m1) relative to the unit's staged window, one byte each, plus flags
-//   .x = m0_0 | m1_0 << 8 | m0_1 << 16 | m1_1 << 24     .y = m0_2 | m1_2 << 8 | flags << 16
-enum { PR_LIVE0 = 1, PR_LIVE1 = 2, PR_EDGE = 4 };
-// one stage of a warp's ring (all 16-byte aligned for the bulk copies)
-struct __align__(16) Stage {
-    float    x[3][CL_WMAX];        // x window of rows r-1, r, r+1
-    float    y[3][CL_WMAX];
-    uint2    pr[32];               // the 32 threads' candidate ranges
-    UnitPlan plan;                 // written by lane 0 before it issues the copies
-};
+enum { ST_PR = 0, ST_PV = 1, ST_REBUILDS = 2, ST_ERR = 3, ST_FLAG = 4, ST_WORDS = 8 };
+enum { CERR_BARRIER = 1, CERR_LIST_OVERFLOW = 2 };
 
 struct CellsArgs {
     PairConsts pc;
-    int   N, Nalloc, G;
+    int   N, Nalloc, G, nchunks;
     int   nrows, nbx, ncells;
-    float inv_hy, inv_wx, half_skin2, dt;
-    float*  X[2];
-    float*  Y[2];
+    float inv_hy, inv_wx, rlist2, half_skin2, dt;
+    float2* R[2];
     float2* V[2];
     int*    orig[2];
     float2* Rb;
     float2* Fs;                     // forces held across the thermostat barrier
-    int *key, *rank, *tmp, *cell_count, *cell_start, *row_tot;
-    int2*     unit_tab;             // (row, first slot) of every unit
-    UnitPlan* plans;                // copy plan of every unit
-    int*      sched;                // [2] dynamic unit counters (by step parity)
-    uint2*    pranges;              // candidate ranges of every slot pair
-    int       maxunits;
-    float  *pe_part, *ke_part;      // [2*maxunits] per-unit partials (by step parity)
+    int *key, *rank, *tmpk, *tmpo, *tmpc, *cell_count, *cell_start, *row_tot;
+    unsigned* meta;
+    uint2*    ent;
+    int4*     wplan;                // per warp of 32 slots: 2 x int4 (window starts / lengths, flag)
+    float  *pe_part, *ke_part;      // [2*nchunks] per-chunk partials (by step parity)
     int*      state;                // ST_* words
     unsigned* bar;
     const float2* R_in;
@@ -124,10 +81,6 @@ struct CellsArgs {
     long long* prof;                // optional [G][12] phase clocks (debug: LJMD_CELLS_PROF=1)
     float   count_r2;
 };
-
-__device__ __forceinline__ float pad_x(int row, int nrows) {
-    return CL_SENT * (1.0f + (float)row / (float)nrows);
-}
 
 // one fp32 multiply then truncation (x >= 0); the clamp handles x == box (MD:72 closed range)
 __device__ __forceinline__ int strip_coord(float x, float inv, int n) {
@@ -163,411 +116,6 @@ __device__ __forceinline__ int block_exscan(int v, int* swarp /* CL_THREADS/32 +
     return inc - v + swarp[w];
 }
 
-struct Ctx {
-    unsigned epoch;
-    unsigned uses;      // this warp's ring: units consumed so far (stage = uses % CL_NST)
-    unsigned phase;     // bit s = parity of the next completion of stage s's mbarrier
-    int pr, pv, ntot, nunits;
-    long long* pt;      // shared-memory phase clocks (thread 0), or nullptr
-};
-
-#define CL_PROF(k)                                                          \
-    do {                                                                    \
-        if (ctx.pt && threadIdx.x == 0) {                                   \
-            long long _t = clock64();                                       \
-            ctx.pt[k] += _t - ctx.pt[11];                                   \
-            ctx.pt[11] = _t;                                                \
-        }                                                                   \
-    } while (0)
-
-#define CL_BARRIER() grid_barrier(a.bar, (++ctx.epoch) * (unsigned)a.G, a.state + ST_ERR)
-
-// ---- rebuild: counting sort by cell, row-structured index, deterministic in-cell order -----------
-__device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan) {
-    const int tid = threadIdx.x, gtid = blockIdx.x * CL_THREADS + tid, gsz = a.G * CL_THREADS;
-    const float* __restrict__ Xc = a.X[ctx.pr];
-    const float* __restrict__ Yc = a.Y[ctx.pr];
-    const int* __restrict__ orig_old = a.orig[ctx.pv];
-    const int ntot_old = ctx.ntot;
-    CL_PROF(0);
-    // B1: cell of every live slot + histogram; the atomic's return value is the slot's (arbitrary)
-    //     arrival rank inside its cell, so the scatter needs no second atomic pass.
-    //     (cell_count is all-zero on entry: cleared at create and again by B3 of every rebuild.)
-    for (int k = gtid; k < ntot_old; k += gsz) {
-        int c = -1;
-        if (orig_old[k] >= 0) {
-            c = strip_coord(Yc[k], a.inv_hy, a.nrows) * a.nbx + strip_coord(Xc[k], a.inv_wx, a.nbx);
-            a.rank[k] = atomicAdd(&a.cell_count[c], 1);
-        }
-        a.key[k] = c;
-    }
-    CL_BARRIER();
-    CL_PROF(2);
-    // B2: population of every row
-    for (int r = blockIdx.x; r < a.nrows; r += a.G) {
-        int s = 0;
-        for (int b = tid; b < a.nbx; b += CL_THREADS) s += a.cell_count[r * a.nbx + b];
-        int tot;
-        (void)block_exscan(s, sscan, &tot);
-        if (tid == 0) a.row_tot[r] = tot;
-    }
-    CL_BARRIER();
-    CL_PROF(3);
-    // B3: row offsets (every row starts on a multiple of 4 slots) + in-row exclusive scan ->
-    //     cell_start; the row is padded with sentinel slots; its counters are cleared for the next rebuild.
-    {
-        float* Xn = a.X[ctx.pr ^ 1];
-        float* Yn = a.Y[ctx.pr ^ 1];
-        int* on = a.orig[ctx.pv ^ 1];
-        for (int r = blockIdx.x; r < a.nrows; r += a.G) {
-            int s = 0, sc = 0;
-            for (int q = tid; q < r; q += CL_THREADS) {
-                const int len = (a.row_tot[q] + 3) & ~3;
-                s += len;
-                sc += (len + CL_UNIT - 1) / CL_UNIT;
-            }
-            int carry, chunk0;
-            (void)block_exscan(s, sscan, &carry);
-            (void)block_exscan(sc, sscan, &chunk0);
-            const int rtot = a.row_tot[r];
-            const int row0 = carry;
-            // the row's units: consecutive runs of CL_UNIT slots, never straddling a row
-            {
-                const int len = (rtot + 3) & ~3, nch = (len + CL_UNIT - 1) / CL_UNIT;
-                for (int j = tid; j < nch; j += CL_THREADS) a.unit_tab[chunk0 + j] = make_int2(r, row0 + j * CL_UNIT);
-                if (r == a.nrows - 1 && tid == 0) a.state[ST_NUNITS] = chunk0 + nch;
-            }
-            for (int bb = 0; bb < a.nbx; bb += CL_THREADS) {
-                const int b = bb + tid;
-                int v = 0;
-                if (b < a.nbx) { v = a.cell_count[r * a.nbx + b]; a.cell_count[r * a.nbx + b] = 0; }
-                int tot;
-                const int ex = block_exscan(v, sscan, &tot);
-                if (b < a.nbx) a.cell_start[r * a.nbx + b] = carry + ex;
-                carry += tot;
-            }
-            // pad the row to a multiple of 4 slots with sentinel slots, each at its own place
-            if (tid < ((rtot + 3) & ~3) - rtot) {
-                const int pad = row0 + rtot + tid;
-                a.tmp[pad] = -1; on[pad] = -1;
-                Xn[pad] = pad_x(r, a.nrows); Yn[pad] = CL_SENT * (1.0f + 0.125f * (float)tid);
-                a.Rb[pad] = make_float2(CL_SENT, CL_SENT);
-                a.V[ctx.pv ^ 1][pad] = make_float2(0.0f, 0.0f);
-            }
-            if (r == a.nrows - 1 && tid == 0) a.cell_start[a.ncells] = row0 + ((rtot + 3) & ~3);
-        }
-    }
-    CL_BARRIER();
-    CL_PROF(4);
-    // B4: scatter source slots into their cell's range (arrival order inside a cell)
-    for (int k = gtid; k < ntot_old; k += gsz) {
-        const int c = a.key[k];
-        if (c >= 0) a.tmp[a.cell_start[c] + a.rank[k]] = k;
-    }
-    CL_BARRIER();
-    CL_PROF(5);
-    // B5: each new slot picks the member of its cell whose ORIGINAL index has the slot's rank, so
-    //     the sorted order (cell, orig) is a pure function of the positions (bit-reproducible
-    //     summation order downstream), then gathers that member's state (coalesced writes).
-    //     (A bin holds ~1.6 particles at liquid density; a bin with more than CL_ORDER_MAX members
-    //     keeps its arrival order: still correct, no longer run-to-run bit-reproducible.)
-    {
-        const int ntot_new = a.cell_start[a.ncells];
-        float* Xn = a.X[ctx.pr ^ 1];
-        float* Yn = a.Y[ctx.pr ^ 1];
-        const float2* Vo = a.V[ctx.pv];
-        float2* Vn = a.V[ctx.pv ^ 1];
-        int* on = a.orig[ctx.pv ^ 1];
-        for (int d = gtid; d < ntot_new; d += gsz) {
-            const int k = a.tmp[d];
-            if (k < 0) continue;                                  // pad slot (initialised in B3)
-            const int c = a.key[k];
-            const int b = a.cell_start[c], n = a.cell_start[c + 1] - b, p = d - b;
-            int ksel = k;
-            if (n > 1 && n <= CL_ORDER_MAX) {
-                for (int m = 0; m < n; ++m) {
-                    const int km = a.tmp[b + m];
-                    if (km < 0) continue;                         // the row's pad sits in its last bin
-                    const int om = orig_old[km];
-                    int rk = 0;
-                    for (int q = 0; q < n; ++q) {
-                        const int kq = a.tmp[b + q];
-                        rk += (kq >= 0 && orig_old[kq] < om);
-                    }
-                    if (rk == p) { ksel = km; break; }
-                }
-            }
-            const float x = Xc[ksel], y = Yc[ksel];
-            Xn[d] = x; Yn[d] = y;
-            a.Rb[d] = make_float2(x, y);
-            Vn[d] = Vo[ksel];
-            on[d] = orig_old[ksel];
-        }
-        ctx.ntot = ntot_new;
-        ctx.nunits = __ldcg(a.state + ST_NUNITS);
-    }
-    ctx.pr ^= 1;
-    ctx.pv ^= 1;
-    if (blockIdx.x == 0 && tid == 0) a.state[ST_REBUILDS] += 1;
-    CL_BARRIER();
-    CL_PROF(6);
-    // B6: per unit (one warp each) the copy plan, per thread of the unit its candidate ranges: both
-    //     depend only on the build-time structure, so the per-step pass does no index arithmetic.
-    //     Window k = bins [bf-K, bl+K] of row r+k-1 (periodic in r, clipped in x), aligned outwards
-    //     to 4 slots; a thread's range k = bins [b0-K, b1+K] of that row, as slot pairs relative to
-    //     the window.  Edge threads (wrapped ranges) and oversized units are flagged instead.
-    {
-        const int* __restrict__ cs = a.cell_start;
-        const int lane = tid & 31;
-        const int W = a.G * CL_WARPS, gw = blockIdx.x * CL_WARPS + (tid >> 5);
-        for (int u = gw; u < ctx.nunits; u += W) {
-            const int2 tab = a.unit_tab[u];
-            const int row = tab.x, slot0 = tab.y;
-            const int rend = cs[(row + 1) * a.nbx];                    // next row's first slot (even)
-            const int n = min(CL_UNIT, rend - slot0);
-            const int bf = strip_coord(a.Rb[slot0].x, a.inv_wx, a.nbx);
-            const int bl = strip_coord(a.Rb[slot0 + n - 1].x, a.inv_wx, a.nbx);   // a pad clamps to the last bin
-            const int lo = max(bf - CL_K, 0), hi = min(bl + CL_K, a.nbx - 1);
-            int ws[3], nw[3];
-            bool direct = false;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                int rr = row + k - 1;
-                rr += (rr < 0) ? a.nrows : 0;
-                rr -= (rr >= a.nrows) ? a.nrows : 0;
-                ws[k] = cs[rr * a.nbx + lo] & ~3;
-                nw[k] = ((cs[rr * a.nbx + hi + 1] + 3) & ~3) - ws[k];
-                direct |= (nw[k] > CL_WMAX);
-            }
-            if (lane == 0) {
-                UnitPlan pl;
-                pl.row = row; pl.slot0 = slot0; pl.direct = direct ? 1 : 0;
-                pl.n = n | (direct ? 0 : nw[2] << 16);
-                pl.ws[0] = ws[0]; pl.ws[1] = ws[1]; pl.ws[2] = ws[2];
-                pl.nw01 = direct ? 0 : (nw[0] | nw[1] << 16);
-                a.plans[u] = pl;
-            }
-            // this lane's slot pair
-            const int p = (slot0 >> 1) + lane;
-            if (2 * lane < n) {
-                const float4 rb = reinterpret_cast<const float4*>(a.Rb)[p];
-                const bool live0 = rb.x < 0.5f * CL_SENT, live1 = rb.z < 0.5f * CL_SENT;
-                unsigned flags = (live0 ? PR_LIVE0 : 0) | (live1 ? PR_LIVE1 : 0);
-                uint2 w = make_uint2(0u, 0u);
-                if (live0) {
-                    const int b0 = strip_coord(rb.x, a.inv_wx, a.nbx);
-                    const int b1 = live1 ? strip_coord(rb.z, a.inv_wx, a.nbx) : b0;
-                    const bool edge = (row == 0) | (row == a.nrows - 1) | (b0 < CL_K) | (b1 > a.nbx - 1 - CL_K);
-                    if (edge) {
-                        flags |= PR_EDGE;
-                    } else if (!direct) {
-                        unsigned m[6];
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            const int s = cs[(row + k - 1) * a.nbx + b0 - CL_K];
-                            const int e = cs[(row + k - 1) * a.nbx + b1 + CL_K + 1];
-                            m[2 * k]     = (unsigned)((s >> 1) - (ws[k] >> 1));
-                            m[2 * k + 1] = (unsigned)(((e + 1) >> 1) - (ws[k] >> 1));
-                        }
-                        w.x = m[0] | m[1] << 8 | m[2] << 16 | m[3] << 24;
-                        w.y = m[4] | m[5] << 8;
-                    }
-                }
-                w.y |= flags << 16;
-                a.pranges[p] = w;
-            }
-        }
-    }
-    CL_BARRIER();
-    CL_PROF(7);
-}
-
-// ---- packed pair evaluation ------------------------------------------------------------------------
-// A thread owns the adjacent slots i0 = 2p, i1 = 2p+1 (packed as xi2 = (x_i0, x_i1)).  One iteration
-// loads the x and y of the two adjacent candidate slots j0 = 2m, j1 = 2m+1 as two 64-bit loads and
-// evaluates FOUR pairs on the packed FP32x2 pipe with no register shuffling:
-//   "straight" set (i0,j0),(i1,j1) from xi2, "swapped" set (i1,j0),(i0,j1) from the swapped copy
-//   (x_i1, x_i0) (an operand swizzle of FADD2, not a register move).
-// d is formed as xj - xi (= -(xi - xj) exactly), so the accumulators hold -F bit for bit.
-//   r2 = dx*dx + dy*dy unfused (fma(t, 1, u) with a run-time 1: see pair2_accum) => the pair set
-//   {r2 < rc2} is the oracle's.
-//   LJMD_CELLS_RCP_PRODUCT: 1/r2 of the two pairs of a set from ONE MUFU.RCP of the product
-//   (ir2_a = r2_b * rcp(r2_a * r2_b)): MUFU issues at 1/8 rate and would otherwise co-limit the loop.
-// KEEP:   per-pair keep predicates are applied (self pair of the own row; exact bounds of edge ranges).
-// MINIMG: exact minimum image on every displacement (edge warps).
-// The cutoff is a select on the ALU pipe (FSETP + SEL): the FMA pipe is the one that saturates (a
-// packed FP32x2 instruction occupies it for two cycles), so nothing that can run elsewhere is put on
-// it; the select also discards the NaN of a masked 0 * inf.
-template <bool PE, bool MINIMG, bool KEEP>
-__device__ __forceinline__ void eval_set(const PairConsts& pc, const PairConsts2& c2, float2 nxi,
-                                         float2 nyi, float2 xj, float2 yj, bool keepx, bool keepy,
-                                         float2& ax, float2& ay, float2& pe2) {
-    float2 dx = __fadd2_rn(xj, nxi);
-    float2 dy = __fadd2_rn(yj, nyi);
-    if (MINIMG) {
-        dx.x = min_image(dx.x, pc.box, pc.timg); dx.y = min_image(dx.y, pc.box, pc.timg);
-        dy.x = min_image(dy.x, pc.box, pc.timg); dy.y = min_image(dy.y, pc.box, pc.timg);
-    }
-    const float2 r2 = __ffma2_rn(__fmul2_rn(dx, dx), c2.one, __fmul2_rn(dy, dy));
-    float2 ir2;
-#if LJMD_CELLS_RCP_PRODUCT
-    const float rp = rcp_approx(__fmul_rn(r2.x, r2.y));
-    ir2 = __fmul2_rn(make_float2(r2.y, r2.x), make_float2(rp, rp));
-#else
-    ir2 = make_float2(rcp_approx(r2.x), rcp_approx(r2.y));
-#endif
-    if (KEEP) {
-        ir2.x = (keepx & (r2.x < pc.rc2)) ? ir2.x : 0.0f;
-        ir2.y = (keepy & (r2.y < pc.rc2)) ? ir2.y : 0.0f;
-    } else {
-        ir2.x = (r2.x < pc.rc2) ? ir2.x : 0.0f;
-        ir2.y = (r2.y < pc.rc2) ? ir2.y : 0.0f;
-    }
-    const float2 ir6 = __fmul2_rn(__fmul2_rn(ir2, ir2), ir2);
-    const float2 f = __fmul2_rn(__ffma2_rn(ir6, c2.c12, c2.nc6), __fmul2_rn(ir6, ir2));
-    ax = __ffma2_rn(f, dx, ax);
-    ay = __ffma2_rn(f, dy, ay);
-    if (PE) pe2 = __ffma2_rn(ir6, __ffma2_rn(ir6, c2.d12, c2.nd6), pe2);
-}
-
-struct PairAcc {
-    float2 axA, ayA, axB, ayB, peA, peB;
-};
-
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
-
-// interior: slots [2*m0, 2*m1) (range aligned outwards to slot pairs: the extra slots belong to the
-// same row and to bins outside the stencil, hence beyond rc, and to no other range of this thread).
-// pself = the thread's own slot pair if this is its own row, else -1.  ONE instance of this loop
-// serves all three rows (it is the hot code: it has to stay inside the instruction cache).
-template <bool PE>
-__device__ __forceinline__ void row_range(const PairConsts& pc, const PairConsts2& c2,
-                                          const float2* __restrict__ X2, const float2* __restrict__ Y2,
-                                          int m0, int m1, int pself, float2 nxi, float2 nyi, float2 nxs,
-                                          float2 nys, PairAcc& acc) {
-#pragma unroll CL_UNROLL
-    for (int m = m0; m < m1; ++m) {
-        const float2 xj = X2[m], yj = Y2[m];
-        const bool k = (m != pself);
-        eval_set<PE, false, true >(pc, c2, nxi, nyi, xj, yj, k, k, acc.axA, acc.ayA, acc.peA);
-        eval_set<PE, false, false>(pc, c2, nxs, nys, xj, yj, true, true, acc.axB, acc.ayB, acc.peB);
-    }
-}
-
-// edge: slots [s, e) exactly, minimum image, any candidate may be one of the thread's own slots
-// (rare path: kept out of line, generic pointers — the window may be shared or global memory)
-template <bool PE>
-__device__ __noinline__ void edge_range(const PairConsts& pc, const PairConsts2& c2,
-                                        const float2* X2, const float2* Y2,
-                                        int s, int e, int p, float2 nxi, float2 nyi, float2 nxs,
-                                        float2 nys, PairAcc& acc) {
-    for (int m = s >> 1; m < ((e + 1) >> 1); ++m) {
-        const float2 xj = X2[m], yj = Y2[m];
-        const bool v0 = (2 * m >= s), v1 = (2 * m + 1 < e), own = (m == p);
-        eval_set<PE, true, true>(pc, c2, nxi, nyi, xj, yj, v0 & !own, v1 & !own, acc.axA, acc.ayA, acc.peA);
-        eval_set<PE, true, true>(pc, c2, nxs, nys, xj, yj, v0, v1, acc.axB, acc.ayB, acc.peB);
-    }
-}
-
-// ---- scalar path (count mode only) ---------------------------------------------------------------
-// One particle against bins [b-K, b+K] of rows r-1, r, r+1 with periodic wrap of both indices: up to
-// two pieces per row, exact bounds, scalar arithmetic with the exact minimum image.
-template <bool PE, bool COUNT>
-__device__ __forceinline__ void generic_particle(const CellsArgs& a, const float* __restrict__ X,
-                                                 const float* __restrict__ Y, int i, float xi, float yi,
-                                                 int r, int b, float lim2, float& fx, float& fy,
-                                                 float& pe, int& cnt) {
-    const PairConsts pc = a.pc;
-    const int* __restrict__ cs = a.cell_start;
-    for (int dr = -1; dr <= 1; ++dr) {
-        int rr = r + dr;
-        rr += (rr < 0) ? a.nrows : 0;
-        rr -= (rr >= a.nrows) ? a.nrows : 0;
-        const int lo = b - CL_K, hi = b + CL_K;
-        for (int piece = 0; piece < 3; ++piece) {
-            int bl, bh;
-            if (piece == 0)      { bl = max(lo, 0); bh = min(hi, a.nbx - 1); }
-            else if (piece == 1) { if (lo >= 0) continue; bl = lo + a.nbx; bh = a.nbx - 1; }
-            else                 { if (hi < a.nbx) continue; bl = 0; bh = hi - a.nbx; }
-            const int s = cs[rr * a.nbx + bl], e = cs[rr * a.nbx + bh + 1];
-            for (int j = s; j < e; ++j) {
-                if (j == i) continue;
-                const float xj = X[j], yj = Y[j];
-                if (COUNT) {
-                    const float dx = min_image(__fsub_rn(xi, xj), pc.box, pc.timg);
-                    const float dy = min_image(__fsub_rn(yi, yj), pc.box, pc.timg);
-                    const float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-                    cnt += (r2 < lim2);
-                } else {
-                    pair_accum<true, PE, false>(xi, yi, xj, yj, true, pc, fx, fy, pe);
-                }
-            }
-        }
-    }
-}
-
-// velocity-Verlet epilogue of one particle (MD:70-74) + outputs; returns "left the skin/2 ball"
-struct StepFlags {
-    bool kick1, final, want_e, thermo, sample;
-    long long s;
-};
-
-__device__ __forceinline__ bool finish_particle(const CellsArgs& a, const StepFlags& f, int slot, int o,
-                                                float rx, float ry, float Fx, float Fy, float2& v,
-                                                float2 rb, float& xn, float& yn, float& ke_thread) {
-    const RunCtl& rc = a.rc;
-    xn = rx; yn = ry;
-    if (f.kick1) { v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt); }                      // MD:74
-    if (f.want_e || f.thermo) ke_thread += v.x * v.x + v.y * v.y;
-    if (f.sample) rc.traj[(size_t)(f.s / rc.sample_every) * a.N + o] = make_float2(rx, ry);      // MD:93-100
-    if (f.thermo) {
-        a.Fs[slot] = make_float2(Fx, Fy);
-        return false;
-    }
-    if (f.final) {
-        if (a.R_out) a.R_out[o] = make_float2(rx, ry);
-        if (a.V_out) a.V_out[o] = v;
-        if (a.F_out) a.F_out[o] = make_float2(Fx, Fy);
-        return false;
-    }
-    v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt);                                        // MD:70
-    xn = drift(rx, v.x, a.dt, a.pc.box);                                                         // MD:71-72
-    yn = drift(ry, v.y, a.dt, a.pc.box);
-    const float ddx = min_image(__fsub_rn(xn, rb.x), a.pc.box, a.pc.timg);
-    const float ddy = min_image(__fsub_rn(yn, rb.y), a.pc.box, a.pc.timg);
-    return ddx * ddx + ddy * ddy > a.half_skin2;
-}
-
-// ---- mbarrier / TMA bulk-copy primitives (sm_90+ PTX; SASS: SYNCS.*, UBLKCP) ------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// global -> shared bulk copy (bytes and both addresses multiples of 16), completion on `bar`
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-// order generic-proxy accesses (the previous step's st.global, made visible by the grid barrier)
-// against the async proxy (the bulk copies that read them)
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // sum of n floats in fixed order by the whole CTA, in double; result valid in every thread
 __device__ __forceinline__ double block_sum_array(const float* p, int n, double* sdbl /* CL_THREADS/32 */) {
     double t = 0.0;
@@ -582,326 +130,467 @@ __device__ __forceinline__ double block_sum_array(const float* p, int n, double*
     return tot;
 }
 
-// ---- lane 0: issue the bulk copies of one unit into a stage of the warp's ring ---------------------
-struct PlanRegs { int4 q0, q1; };
-__device__ __forceinline__ PlanRegs load_plan(const CellsArgs& a, int u) {
-    const int4* __restrict__ pg = reinterpret_cast<const int4*>(a.plans + u);
-    PlanRegs q;
-    q.q0 = pg[0]; q.q1 = pg[1];
-    return q;
-}
-__device__ __forceinline__ void issue_unit(const CellsArgs& a, const Ctx& ctx, const PlanRegs& q, Stage& st,
-                                           unsigned long long* full) {
-    int4* ps = reinterpret_cast<int4*>(&st.plan);
-    ps[0] = q.q0; ps[1] = q.q1;
-    if (q.q0.w) return;                                  // direct unit: nothing staged
-    const float* __restrict__ X = a.X[ctx.pr];
-    const float* __restrict__ Y = a.Y[ctx.pr];
-    const int ws[3] = {q.q1.x, q.q1.y, q.q1.z};
-    const int nw[3] = {q.q1.w & 0xffff, (int)((unsigned)q.q1.w >> 16), (int)((unsigned)q.q0.z >> 16)};
-    const int slot0 = q.q0.y;
-    unsigned bytes = 32u * 8u;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) bytes += (unsigned)nw[k] * 8u;
-    mbar_arrive_expect_tx(full, bytes);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        if (nw[k] > 0) {
-            bulk_g2s(st.x[k], X + ws[k], (unsigned)nw[k] * 4u, full);
-            bulk_g2s(st.y[k], Y + ws[k], (unsigned)nw[k] * 4u, full);
-        }
-    }
-    bulk_g2s(st.pr, a.pranges + (slot0 >> 1), 32u * 8u, full);
-}
+struct Ctx {
+    unsigned epoch;
+    int pr, pv;
+    long long* pt;      // shared-memory phase clocks (thread 0), or nullptr
+};
 
-// dynamic schedule: lane 0 draws the next unit from a per-step counter (one atomic per unit, issued
-// two units ahead of its use); -1 = no more units
-__device__ __forceinline__ int next_unit(const CellsArgs& a, const Ctx& ctx, int par) {
-    const int u = atomicAdd(&a.sched[par], 1);
-    return (u < ctx.nunits) ? u : -1;
-}
+#define CL_PROF(k)                                                          \
+    do {                                                                    \
+        if (ctx.pt && threadIdx.x == 0) {                                   \
+            long long _t = clock64();                                       \
+            ctx.pt[k] += _t - ctx.pt[11];                                   \
+            ctx.pt[11] = _t;                                                \
+        }                                                                   \
+    } while (0)
 
-// ---- forces + integrate of one unit (one warp) ------------------------------------------------------
-template <bool PE, bool STAGED>
-__device__ __forceinline__ void unit_compute(const CellsArgs& a, const Ctx& ctx, const StepFlags& fl,
-                                             const Stage& st, float& pe_thread, float& ke_thread,
-                                             int& moved) {
-    const UnitPlan& m = st.plan;                       // (in shared memory)
-    const int t = threadIdx.x & 31;
-    const PairConsts pc = a.pc;
-    const PairConsts2 c2 = make_pair_consts2(pc);
-    const float2* __restrict__ X2g = reinterpret_cast<const float2*>(a.X[ctx.pr]);
-    const float2* __restrict__ Y2g = reinterpret_cast<const float2*>(a.Y[ctx.pr]);
-    float2* Xn2 = reinterpret_cast<float2*>(a.X[ctx.pr ^ 1]);
-    float2* Yn2 = reinterpret_cast<float2*>(a.Y[ctx.pr ^ 1]);
-    float4* V4 = reinterpret_cast<float4*>(a.V[ctx.pv]);
-    const int* __restrict__ csg = a.cell_start;
-    const int  slot0 = m.slot0, nslots = m.n & 0xffff, r = m.row;
-    const int  p = (slot0 >> 1) + t;                   // global slot-pair index
-    const bool act = 2 * t < nslots;
-    float2 xi = make_float2(CL_SENT, CL_SENT), yi = xi;
-    float4 rb = make_float4(CL_SENT, CL_SENT, CL_SENT, CL_SENT);
-    float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    int2 o = make_int2(-1, -1);
-    uint2 pr = make_uint2(0u, 0u);
-    if (act) {
-        // build positions, velocities and original indices are only needed by the epilogue: plain
-        // coalesced loads, issued now, consumed after the pair loop
-        rb = reinterpret_cast<const float4*>(a.Rb)[p];
-        o = reinterpret_cast<const int2*>(a.orig[ctx.pv])[p];
-        if (a.rc.nsteps > 0) v = V4[p];
-        if (STAGED) {
-            const int q = p - (m.ws[1] >> 1);
-            pr = st.pr[t];
-            xi = reinterpret_cast<const float2*>(st.x[1])[q];
-            yi = reinterpret_cast<const float2*>(st.y[1])[q];
-        } else {
-            pr = a.pranges[p];
-            xi = X2g[p]; yi = Y2g[p];
-        }
-    }
-    const unsigned flags = pr.y >> 16;
-    const bool live0 = (flags & PR_LIVE0) != 0, live1 = (flags & PR_LIVE1) != 0;
-    const bool wedge = __any_sync(0xffffffffu, (flags & PR_EDGE) != 0);
-    PairAcc acc;
-    acc.axA = acc.ayA = acc.axB = acc.ayB = acc.peA = acc.peB = make_float2(0.0f, 0.0f);
-    const float2 nxi = make_float2(-xi.x, -xi.y), nyi = make_float2(-yi.x, -yi.y);
-    const float2 nxs = make_float2(-xi.y, -xi.x), nys = make_float2(-yi.y, -yi.x);
-    if (STAGED && !wedge) {
-        // the common case: three precomputed ranges, straight out of the staged windows
-        if (live0) {
-            const unsigned long long w = (unsigned long long)pr.x | ((unsigned long long)(pr.y & 0xffffu) << 32);
-#pragma unroll 1
-            for (int k = 0; k < 3; ++k) {       // rows r-1, r, r+1: one contiguous range each
-                const int m0 = (int)((w >> (16 * k)) & 0xffu), m1 = (int)((w >> (16 * k + 8)) & 0xffu);
-                const int pself = (k == 1) ? p - (m.ws[1] >> 1) : -1;
-                row_range<PE>(pc, c2, reinterpret_cast<const float2*>(st.x[k]),
-                              reinterpret_cast<const float2*>(st.y[k]), m0, m1, pself, nxi, nyi, nxs, nys, acc);
+#define CL_BARRIER() grid_barrier(a.bar, (++ctx.epoch) * (unsigned)a.G, a.state + ST_ERR)
+
+// ---- rebuild: counting sort by cell, deterministic in-cell order, bitmask Verlet list --------------
+// lim2: list radius squared (rc + skin for a run, the caller's radius in count mode)
+__device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float lim2) {
+    const int tid = threadIdx.x, gtid = blockIdx.x * CL_THREADS + tid, gsz = a.G * CL_THREADS;
+    const float2* __restrict__ Rc = a.R[ctx.pr];
+    const int* __restrict__ orig_old = a.orig[ctx.pv];
+    const int N = a.N;
+    CL_PROF(0);
+    // B1: cell of every particle + histogram; the atomic's return value is the particle's (arbitrary)
+    //     arrival rank inside its cell, so the scatter needs no second atomic pass.  Four particles
+    //     per thread keep four atomics in flight.
+    //     (cell_count is all-zero on entry: cleared at create and again by B3 of every rebuild.)
+    for (int k0 = gtid; k0 < N; k0 += 4 * gsz) {
+        int c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * gsz;
+            c[u] = -1;
+            if (k < N) {
+                const float2 r = Rc[k];
+                c[u] = strip_coord(r.y, a.inv_hy, a.nrows) * a.nbx + strip_coord(r.x, a.inv_wx, a.nbx);
             }
         }
-    } else if (live0) {
-        // edge warps and oversized units: ranges from the global cell index, positions from global
-        const int b0 = strip_coord(rb.x, a.inv_wx, a.nbx);
-        const int b1 = live1 ? strip_coord(rb.z, a.inv_wx, a.nbx) : b0;
-        if (!wedge) {
-#pragma unroll 1
-            for (int k = 0; k < 3; ++k) {
-                const int s = csg[(r + k - 1) * a.nbx + b0 - CL_K], e = csg[(r + k - 1) * a.nbx + b1 + CL_K + 1];
-                row_range<PE>(pc, c2, X2g, Y2g, s >> 1, (e + 1) >> 1, (k == 1) ? p : -1, nxi, nyi, nxs, nys, acc);
+        int rk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) rk[u] = (c[u] >= 0) ? atomicAdd(&a.cell_count[c[u]], 1) : 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * gsz;
+            if (k < N) { a.key[k] = c[u]; a.rank[k] = rk[u]; }
+        }
+    }
+    CL_BARRIER();
+    CL_PROF(2);
+    // B2: population of every row
+    for (int r = blockIdx.x; r < a.nrows; r += a.G) {
+        int s = 0;
+        for (int b = tid; b < a.nbx; b += CL_THREADS) s += a.cell_count[r * a.nbx + b];
+        int tot;
+        (void)block_exscan(s, sscan, &tot);
+        if (tid == 0) a.row_tot[r] = tot;
+    }
+    CL_BARRIER();
+    CL_PROF(3);
+    // B3: row offsets + in-row exclusive scan -> cell_start; the row's counters are cleared for the
+    //     next rebuild.
+    for (int r = blockIdx.x; r < a.nrows; r += a.G) {
+        int s = 0;
+        for (int q = tid; q < r; q += CL_THREADS) s += a.row_tot[q];
+        int carry;
+        (void)block_exscan(s, sscan, &carry);
+        for (int bb = 0; bb < a.nbx; bb += CL_THREADS) {
+            const int b = bb + tid;
+            int v = 0;
+            if (b < a.nbx) { v = a.cell_count[r * a.nbx + b]; a.cell_count[r * a.nbx + b] = 0; }
+            int tot;
+            const int ex = block_exscan(v, sscan, &tot);
+            if (b < a.nbx) a.cell_start[r * a.nbx + b] = carry + ex;
+            carry += tot;
+        }
+        if (r == a.nrows - 1 && tid == 0) a.cell_start[a.ncells] = carry;
+    }
+    CL_BARRIER();
+    CL_PROF(4);
+    // B4: scatter (source slot, original index, cell) into the cell's slot range, arrival order
+    for (int k0 = gtid; k0 < N; k0 += 4 * gsz) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * gsz;
+            if (k < N) {
+                const int c = a.key[k];
+                const int d = a.cell_start[c] + a.rank[k];
+                a.tmpk[d] = k;
+                a.tmpo[d] = orig_old[k];
+                a.tmpc[d] = c;
             }
-        } else {
-            // bins [b0-K, b1+K] of rows r-1, r, r+1 with periodic wrap of both indices: one piece plus
-            // up to two wrapped pieces per row (the whole row once if the union would overlap itself)
-            int lo = b0 - CL_K, hi = b1 + CL_K;
-            if (hi - lo + 1 > a.nbx) { lo = 0; hi = a.nbx - 1; }
-#pragma unroll 1
+        }
+    }
+    CL_BARRIER();
+    CL_PROF(5);
+    // B5: each new slot picks the member of its cell whose ORIGINAL index has the slot's rank, so
+    //     the sorted order (cell, orig) is a pure function of the positions (bit-reproducible
+    //     summation order downstream), then gathers that member's state (coalesced writes).
+    //     (A bin holds ~1.6 particles at liquid density; a bin with more than CL_ORDER_MAX members
+    //     keeps its arrival order: still correct, no longer run-to-run bit-reproducible.)
+    {
+        float2* Rn = a.R[ctx.pr ^ 1];
+        const float2* Vo = a.V[ctx.pv];
+        float2* Vn = a.V[ctx.pv ^ 1];
+        int* on = a.orig[ctx.pv ^ 1];
+        for (int d = gtid; d < N; d += gsz) {
+            const int c = a.tmpc[d];
+            const int b = a.cell_start[c], n = a.cell_start[c + 1] - b, p = d - b;
+            int msel = p;
+            if (n > 1 && n <= CL_ORDER_MAX) {
+                for (int m = 0; m < n; ++m) {
+                    const int om = a.tmpo[b + m];
+                    int rk = 0;
+                    for (int q = 0; q < n; ++q) rk += (a.tmpo[b + q] < om);
+                    if (rk == p) { msel = m; break; }
+                }
+            }
+            const int ksel = a.tmpk[b + msel];
+            const float2 r = Rc[ksel];
+            Rn[d] = r;
+            a.Rb[d] = r;
+            Vn[d] = Vo[ksel];
+            on[d] = a.tmpo[b + msel];
+        }
+    }
+    ctx.pr ^= 1;
+    ctx.pv ^= 1;
+    if (blockIdx.x == 0 && tid == 0) a.state[ST_REBUILDS] += 1;
+    CL_BARRIER();
+    CL_PROF(6);
+    // B6: bitmask Verlet list.  For each stencil row the candidate bins [b-K, b+K] (periodic: up to
+    //     two pieces) form contiguous slot ranges; every 32 slots of a range with at least one
+    //     neighbour (min-image r2 < lim2, same unfused fp32 r2 as the force loop, j != i) become one
+    //     (first slot, mask) entry.  Count mode only counts.
+    //     A warp = 32 consecutive slots.  If they share a row and none needs a wrapped range, all their
+    //     neighbours lie in three windows (bins [b_first-K, b_last+K] of rows r-1, r, r+1): the warp's
+    //     plan records them and its entries are stored relative to the staged copy of the windows.
+    {
+        const float2* __restrict__ R = a.R[ctx.pr];
+        const int* __restrict__ cs = a.cell_start;
+        const PairConsts pc = a.pc;
+        const int lane = tid & 31;
+        for (int i0 = (gtid & ~31); i0 < N; i0 += gsz) {
+            const int i = i0 + lane;
+            const bool live = i < N;
+            float2 ri = make_float2(0.0f, 0.0f);
+            int c = 0;
+            if (live) { ri = R[i]; c = a.tmpc[i]; }
+            const int r = c / a.nbx, b = c - r * a.nbx;
+            const bool edge = (r == 0) | (r == a.nrows - 1) | (b < CL_K) | (b > a.nbx - 1 - CL_K);
+            // warp plan
+            const int nl = min(32, N - i0);
+            const int r_first = __shfl_sync(0xffffffffu, r, 0), r_last = __shfl_sync(0xffffffffu, r, nl - 1);
+            const int b_first = __shfl_sync(0xffffffffu, b, 0), b_last = __shfl_sync(0xffffffffu, b, nl - 1);
+            bool staged = (a.mode == 0) && (r_first == r_last) && !__any_sync(0xffffffffu, live && edge);
+            int ws[3] = {0, 0, 0}, wn[3] = {0, 0, 0};
+            if (staged) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    ws[k] = cs[(r_first + k - 1) * a.nbx + b_first - CL_K];
+                    wn[k] = cs[(r_first + k - 1) * a.nbx + b_last + CL_K + 1] - ws[k];
+                    staged = staged && (wn[k] <= CL_WIN);
+                }
+            }
+            if (lane == 0) {
+                a.wplan[2 * (i0 >> 5)]     = make_int4(ws[0], ws[1], ws[2], staged ? 1 : 0);
+                a.wplan[2 * (i0 >> 5) + 1] = make_int4(wn[0], wn[1], wn[2], 0);
+            }
+            if (!live) continue;
+            const int lo = b - CL_K, hi = b + CL_K;
+            int n = 0, cnt = 0;
             for (int k = 0; k < 3; ++k) {
                 int rr = r + k - 1;
                 rr += (rr < 0) ? a.nrows : 0;
                 rr -= (rr >= a.nrows) ? a.nrows : 0;
-                const int* __restrict__ csr = csg + rr * a.nbx;
-                edge_range<PE>(pc, c2, X2g, Y2g, csr[max(lo, 0)], csr[min(hi, a.nbx - 1) + 1], p, nxi, nyi, nxs, nys, acc);
-                if (lo < 0)      edge_range<PE>(pc, c2, X2g, Y2g, csr[lo + a.nbx], csr[a.nbx], p, nxi, nyi, nxs, nys, acc);
-                if (hi >= a.nbx) edge_range<PE>(pc, c2, X2g, Y2g, csr[0], csr[hi - a.nbx + 1], p, nxi, nyi, nxs, nys, acc);
+                const int* __restrict__ csr = cs + rr * a.nbx;
+                for (int piece = 0; piece < 3; ++piece) {
+                    int bl, bh;
+                    if (piece == 0)      { bl = max(lo, 0); bh = min(hi, a.nbx - 1); }
+                    else if (piece == 1) { if (lo >= 0) continue; bl = lo + a.nbx; bh = a.nbx - 1; }
+                    else                 { if (hi < a.nbx) continue; bl = 0; bh = hi - a.nbx; }
+                    const int s = csr[bl], e = csr[bh + 1];
+                    for (int c0 = s; c0 < e; c0 += 32) {
+                        const int cnum = min(32, e - c0);
+                        unsigned mask = 0u;
+                        for (int t0 = 0; t0 < cnum; t0 += 4) {          // four position loads in flight
+                            float2 rj[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) rj[u] = R[c0 + min(t0 + u, cnum - 1)];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float dx = min_image(__fsub_rn(ri.x, rj[u].x), pc.box, pc.timg);
+                                const float dy = min_image(__fsub_rn(ri.y, rj[u].y), pc.box, pc.timg);
+                                const float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                                if (t0 + u < cnum && r2 < lim2 && c0 + t0 + u != i) mask |= 1u << (t0 + u);
+                            }
+                        }
+                        if (mask) {
+                            // staged warp: window-relative slot (the three windows are laid out back
+                            // to back, CL_WIN slots each); otherwise the absolute slot
+                            const unsigned first = staged ? (unsigned)(k * CL_WIN + c0 - ws[k]) : (unsigned)c0;
+                            if (a.mode == 0 && n < CL_E) a.ent[(size_t)n * a.Nalloc + i] = make_uint2(first, mask);
+                            ++n;
+                            cnt += __popc(mask);
+                        }
+                    }
+                }
+            }
+            if (a.mode == 0) {
+                if (n > CL_E) atomicOr(a.state + ST_ERR, CERR_LIST_OVERFLOW);
+                a.meta[i] = (unsigned)min(n, CL_E) | (edge ? 0x100u : 0u);
+            } else {
+                a.key[i] = cnt;
             }
         }
     }
-    // accumulators hold -F:  i0 <- straight.x + swapped.y,  i1 <- straight.y + swapped.x
-    const float F0x = -(acc.axA.x + acc.axB.y), F0y = -(acc.ayA.x + acc.ayB.y);
-    const float F1x = -(acc.axA.y + acc.axB.x), F1y = -(acc.ayA.y + acc.ayB.x);
-    if (PE) pe_thread += (acc.peA.x + acc.peB.y) + (acc.peA.y + acc.peB.x);
-    if (!act) return;
-    // the epilogue operands were requested before the pair loop; this keeps the compiler from
-    // hoisting their first use (e.g. the sign extension of an index) up to the load
-    asm volatile("" : "+r"(o.x), "+r"(o.y), "+f"(rb.x), "+f"(v.x) :: "memory");
-    float2 v0 = make_float2(v.x, v.y), v1 = make_float2(v.z, v.w);
-    float2 xn = xi, yn = yi;
-    if (live0) moved |= finish_particle(a, fl, 2 * p, o.x, xi.x, yi.x, F0x, F0y, v0, make_float2(rb.x, rb.y), xn.x, yn.x, ke_thread);
-    if (live1) moved |= finish_particle(a, fl, 2 * p + 1, o.y, xi.y, yi.y, F1x, F1y, v1, make_float2(rb.z, rb.w), xn.y, yn.y, ke_thread);
-    if (a.rc.nsteps > 0 && !(fl.final && !fl.thermo)) {
-        V4[p] = make_float4(v0.x, v0.y, v1.x, v1.y);
-        if (!fl.thermo) { Xn2[p] = xn; Yn2[p] = yn; }
-    }
+    CL_BARRIER();
+    CL_PROF(7);
 }
 
-// ---- one step's pass of one warp --------------------------------------------------------------------
-// Software pipeline, three units deep, driven by lane 0: while unit u is evaluated, the bulk copies of
-// the next unit are in flight, the copy plan of the one after is being loaded, and the index of the
-// one after that is being drawn from the step's counter.  Which warp evaluates which unit does not
-// affect any result (energies are per-unit partials).
-template <bool PE>
-__device__ __forceinline__ void warp_force_pass(const CellsArgs& a, Ctx& ctx, const StepFlags& fl,
-                                                Stage* ring /* this warp's CL_NST stages */,
-                                                unsigned long long* full /* this warp's CL_NST barriers */,
-                                                int par, bool want_ke, int& moved) {
-    const int lane = threadIdx.x & 31;
-    int u = -1, un = -1, unn = -1, unnn = -1;            // meaningful in lane 0 only
-    PlanRegs qn;
-    qn.q0 = qn.q1 = make_int4(0, 0, 0, 0);
-    if (lane == 0) {
-        fence_proxy_async();
-        u = next_unit(a, ctx, par);
-        un = (u >= 0) ? next_unit(a, ctx, par) : -1;
-        unn = (un >= 0) ? next_unit(a, ctx, par) : -1;
-        if (u >= 0) {
-            const PlanRegs q = load_plan(a, u);
-            issue_unit(a, ctx, q, ring[ctx.uses % CL_NST], &full[ctx.uses % CL_NST]);
-        }
-        if (un >= 0) qn = load_plan(a, un);
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// ---- per-step pass ----------------------------------------------------------------------------------
+// Two neighbours j0, j1 of ONE particle.  Each displacement (dx, dy) is one packed FP32x2 value made
+// directly from the loaded float2 (no register shuffling); from r2 on, the two NEIGHBOURS share the
+// packed instructions.  d is formed as rj - ri (= -(ri - rj) exactly), so the accumulator holds -F
+// bit for bit; r2 = fl(fl(dx*dx) + fl(dy*dy)) unfused => the pair set {r2 < rc2} is the oracle's.
+// The cutoff is a select on the ALU pipe (FSETP + SEL); `two` masks the second neighbour when the
+// entry had an odd number of neighbours left.
+template <bool PE, bool EDGE>
+__device__ __forceinline__ void eval_two(const PairConsts& pc, const PairConsts2& c2, float2 nri,
+                                         float2 rj0, float2 rj1, bool two, float2& acc, float2& pe2) {
+    float2 d0 = __fadd2_rn(rj0, nri);
+    float2 d1 = __fadd2_rn(rj1, nri);
+    if (EDGE) {
+        d0.x = min_image(d0.x, pc.box, pc.timg); d0.y = min_image(d0.y, pc.box, pc.timg);
+        d1.x = min_image(d1.x, pc.box, pc.timg); d1.y = min_image(d1.y, pc.box, pc.timg);
     }
+    const float2 q0 = __fmul2_rn(d0, d0), q1 = __fmul2_rn(d1, d1);
+    const float r20 = __fadd_rn(q0.x, q0.y), r21 = __fadd_rn(q1.x, q1.y);
+    float2 ir2 = make_float2(rcp_approx(r20), rcp_approx(r21));
+    ir2.x = (r20 < pc.rc2) ? ir2.x : 0.0f;
+    ir2.y = (two & (r21 < pc.rc2)) ? ir2.y : 0.0f;
+    const float2 ir6 = __fmul2_rn(__fmul2_rn(ir2, ir2), ir2);
+    const float2 f = __fmul2_rn(__ffma2_rn(ir6, c2.c12, c2.nc6), __fmul2_rn(ir6, ir2));
+    acc = __ffma2_rn(d0, make_float2(f.x, f.x), acc);
+    acc = __ffma2_rn(d1, make_float2(f.y, f.y), acc);
+    if (PE) pe2 = __ffma2_rn(ir6, __ffma2_rn(ir6, c2.d12, c2.nd6), pe2);
+}
+
+// all neighbours of particle i: the entries are walked as ONE sequence of set bits (a lane that
+// finishes an entry moves on to its next one at once), so a warp runs for the longest LIST, not for
+// the sum of the longest entries.  Every stored entry has a non-empty mask.
+// R = the array the entries index: the staged windows (shared memory) or the global positions
+template <bool PE, bool EDGE>
+__device__ __forceinline__ void list_force(const CellsArgs& a, const float2* R, int i, int n,
+                                           float2 ri, float& Fx, float& Fy, float& pe) {
+    const PairConsts pc = a.pc;
+    const PairConsts2 c2 = make_pair_consts2(pc);
+    const uint2* __restrict__ ep = a.ent + i;
+    const size_t stride = (size_t)a.Nalloc;
+    // the first three entries (all of them, normally) are requested before the loop
+    uint2 e0 = make_uint2(0u, 0u), e1 = e0, e2 = e0;
+    if (n > 0) e0 = ep[0];
+    if (n > 1) e1 = ep[stride];
+    if (n > 2) e2 = ep[2 * stride];
+    const float2 nri = make_float2(-ri.x, -ri.y);
+    float2 acc = make_float2(0.0f, 0.0f), pe2 = acc;
+    unsigned m = e0.y;
+    const float2* base = R + e0.x;
+    int k = 1;
     for (;;) {
-        u = __shfl_sync(0xffffffffu, u, 0);
-        if (u < 0) break;
-        const int s = (int)(ctx.uses % CL_NST);
-        ++ctx.uses;
-        __syncwarp();                                    // every lane is done with the other stage
-        if (lane == 0) {
-            if (unn >= 0) unnn = next_unit(a, ctx, par); // consumed two units from now
-            if (un >= 0) issue_unit(a, ctx, qn, ring[s ^ 1], &full[s ^ 1]);
-            if (unn >= 0) qn = load_plan(a, unn);        // consumed one unit from now
+        if (m == 0u) {
+            if (k >= n) break;
+            const uint2 e = (k == 1) ? e1 : ((k == 2) ? e2 : ep[(size_t)k * stride]);
+            m = e.y;
+            base = R + e.x;
+            ++k;
         }
-        __syncwarp();                                    // plan of unit u (written by lane 0) is visible
-        const Stage& st = ring[s];
-        const bool direct = st.plan.direct != 0;
-        float pe_thread = 0.0f, ke_thread = 0.0f;
-        if (direct) {
-            unit_compute<true, false>(a, ctx, fl, st, pe_thread, ke_thread, moved);
-        } else {
-            mbar_wait(&full[s], (ctx.phase >> s) & 1u);
-            ctx.phase ^= 1u << s;
-            unit_compute<PE, true>(a, ctx, fl, st, pe_thread, ke_thread, moved);
-        }
-        // per-unit energy partials (fixed shuffle tree), reduced in unit order after the barrier
-        if (PE) {
-            const float tsum = warp_sum(pe_thread);
-            if (lane == 0) __stcg(&a.pe_part[par * a.maxunits + u], tsum);
-        }
-        if (want_ke) {
-            const float tsum = warp_sum(ke_thread);
-            if (lane == 0) __stcg(&a.ke_part[par * a.maxunits + u], tsum);
-        }
-        u = un; un = unn; unn = unnn; unnn = -1;
+        const int b0 = 31 - __clz(m);
+        m ^= 1u << b0;
+        const bool two = (m != 0u);
+        const int b1 = two ? 31 - __clz(m) : b0;
+        m &= ~(1u << b1);
+        eval_two<PE, EDGE>(pc, c2, nri, base[b0], base[b1], two, acc, pe2);
     }
+    Fx = -acc.x;
+    Fy = -acc.y;
+    if (PE) pe = pe2.x + pe2.y;
 }
 
-extern __shared__ __align__(128) unsigned char cells_smem[];
-
-__global__ void __launch_bounds__(CL_THREADS, LJMD_CELLS_MINBLOCKS)
+__global__ void __launch_bounds__(CL_THREADS, 2)
 cells_persistent_kernel(const CellsArgs a) {
     __shared__ int    sscan[CL_THREADS / 32 + 1];
+    __shared__ float  sred[CL_THREADS / 32];
     __shared__ double sdbl[CL_THREADS / 32];
     __shared__ float  s_lambda;
     __shared__ long long s_pt[12];
-    __shared__ __align__(8) unsigned long long s_full[CL_WARPS][CL_NST];
-    Stage* stages = reinterpret_cast<Stage*>(cells_smem);
+    __shared__ float2 s_win[CL_WARPS][3 * CL_WIN];      // each warp's staged neighbour windows
     const int tid = threadIdx.x, gtid = blockIdx.x * CL_THREADS + tid, gsz = a.G * CL_THREADS;
-    const int warp = tid >> 5;
     const RunCtl rc = a.rc;
     Ctx ctx;
     ctx.epoch = 0;
-    ctx.uses = 0;
-    ctx.phase = 0;
     ctx.pt = a.prof ? s_pt : nullptr;
-    if (tid == 0) {
-        if (ctx.pt) { for (int k = 0; k < 11; ++k) s_pt[k] = 0; s_pt[11] = clock64(); }
-        for (int w = 0; w < CL_WARPS; ++w)
-            for (int k = 0; k < CL_NST; ++k) mbar_init(&s_full[w][k], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
+    if (ctx.pt && tid == 0) { for (int k = 0; k < 11; ++k) s_pt[k] = 0; s_pt[11] = clock64(); }
     ctx.pr = a.state[ST_PR];
     ctx.pv = a.state[ST_PV];
-    ctx.ntot = a.state[ST_NTOT];
-    ctx.nunits = a.state[ST_NUNITS];
 
     if (a.s_begin < 0) {
-        // load the caller's state (original order, no pads) and sort it
+        // load the caller's state (original order) and sort it
         for (int i = gtid; i < a.N; i += gsz) {
-            const float2 r = a.R_in[i];
-            a.X[ctx.pr][i] = r.x;
-            a.Y[ctx.pr][i] = r.y;
+            a.R[ctx.pr][i] = a.R_in[i];
             a.V[ctx.pv][i] = a.V_in ? a.V_in[i] : make_float2(0.0f, 0.0f);
             a.orig[ctx.pv][i] = i;
         }
-        ctx.ntot = a.N;
         CL_BARRIER();
-        cells_rebuild(a, ctx, sscan);
+        cells_rebuild(a, ctx, sscan, (a.mode == 1) ? a.count_r2 : a.rlist2);
         if (a.mode == 1) {
-            // neighbour recount through the same ranges (scalar path), original order out
-            const float* X = a.X[ctx.pr];
-            const float* Y = a.Y[ctx.pr];
             const int* og = a.orig[ctx.pv];
-            for (int i = gtid; i < ctx.ntot; i += gsz) {
-                const int o = og[i];
-                if (o < 0) continue;
-                const float xi = X[i], yi = Y[i];
-                float fx = 0.0f, fy = 0.0f, pe = 0.0f;
-                int cnt = 0;
-                generic_particle<false, true>(a, X, Y, i, xi, yi, strip_coord(yi, a.inv_hy, a.nrows),
-                                              strip_coord(xi, a.inv_wx, a.nbx), a.count_r2, fx, fy, pe, cnt);
-                a.count_out[o] = cnt;
-            }
-            if (gtid == 0) { a.state[ST_PR] = ctx.pr; a.state[ST_PV] = ctx.pv; a.state[ST_NTOT] = ctx.ntot; }
+            for (int i = gtid; i < a.N; i += gsz) a.count_out[og[i]] = a.key[i];
+            if (gtid == 0) { a.state[ST_PR] = ctx.pr; a.state[ST_PV] = ctx.pv; }
             return;
         }
     }
 
     for (long long s = a.s_begin; s < a.s_end; ++s) {
-        const int par = (int)((s + 1) & 1);
-        StepFlags fl;
-        fl.s      = s;
-        fl.kick1  = (s >= 0);
-        fl.final  = (s == rc.nsteps - 1);
-        fl.want_e = fl.kick1 && rc.energy_every > 0 && (s % rc.energy_every == 0);
-        const bool want_pe = fl.want_e || (rc.nsteps == 0 && a.pe_out != nullptr);
-        fl.thermo = fl.kick1 && rc.thermo_every > 0 && rc.thermo_kT > 0.0f &&
-                    ((s + 1) % rc.thermo_every == 0);
-        fl.sample = fl.kick1 && rc.sample_every > 0 && (s % rc.sample_every == 0) &&
-                    (s / rc.sample_every < rc.S);
+        const int  par     = (int)((s + 1) & 1);
+        const bool kick1   = (s >= 0);
+        const bool final   = (s == rc.nsteps - 1);
+        const bool want_e  = kick1 && rc.energy_every > 0 && (s % rc.energy_every == 0);
+        const bool want_pe = want_e || (rc.nsteps == 0 && a.pe_out != nullptr);
+        const bool thermo  = kick1 && rc.thermo_every > 0 && rc.thermo_kT > 0.0f &&
+                             ((s + 1) % rc.thermo_every == 0);
+        const bool sample  = kick1 && rc.sample_every > 0 && (s % rc.sample_every == 0) &&
+                             (s / rc.sample_every < rc.S);
+        const bool want_ke = want_e || thermo;
         // rebuild requested by the previous step's displacement test?
         if (s > a.s_begin || a.s_begin >= 0) {
-            if (__ldcg(a.state + ST_FLAG) == (int)(s + 1)) cells_rebuild(a, ctx, sscan);
+            if (__ldcg(a.state + ST_FLAG) == (int)(s + 1)) cells_rebuild(a, ctx, sscan, a.rlist2);
         }
-        // the other parity's unit counter is idle during this step: clear it for the next one
-        if (gtid == 0) __stcg(&a.sched[par ^ 1], 0);
+        const float2* __restrict__ R = a.R[ctx.pr];
+        float2*       Rnext = a.R[ctx.pr ^ 1];
+        float2*       V     = a.V[ctx.pv];
+        const int*    og    = a.orig[ctx.pv];
+
         int moved = 0;
-        {
-            const bool want_ke = fl.want_e || fl.thermo;
-            Stage* ring = stages + warp * CL_NST;
-            if (want_pe) warp_force_pass<true >(a, ctx, fl, ring, s_full[warp], par, want_ke, moved);
-            else         warp_force_pass<false>(a, ctx, fl, ring, s_full[warp], par, want_ke, moved);
+        for (int ch = blockIdx.x; ch < a.nchunks; ch += a.G) {
+            const int  i    = ch * CL_THREADS + tid;
+            const bool live = i < a.N;
+            // The pass streams ~70 bytes per particle and a warp has one particle per lane in flight:
+            // without help the SM holds too few bytes in flight to cover the HBM latency.  Request the
+            // NEXT chunk's operands now (L2 -> L1 prefetch); they arrive while this chunk is evaluated.
+            {
+                const int inext = i + a.G * CL_THREADS;
+                if (inext < a.N) {
+                    prefetch_l1(R + inext);
+                    prefetch_l1(a.meta + inext);
+                    prefetch_l1(a.ent + inext);
+                    prefetch_l1(a.ent + (size_t)a.Nalloc + inext);
+                    prefetch_l1(a.ent + 2 * (size_t)a.Nalloc + inext);
+                    if (rc.nsteps > 0) { prefetch_l1(V + inext); prefetch_l1(a.Rb + inext); }
+                    if ((tid & 31) == 0) prefetch_l1(a.wplan + 2 * (inext >> 5));
+                }
+            }
+            float2 ri = make_float2(0.0f, 0.0f);
+            unsigned meta = 0u;                         // dead lanes: interior, no neighbours
+            if (live) { ri = R[i]; meta = a.meta[i]; }
+            const int n = meta & 0xff;
+            const bool wedge = __any_sync(0xffffffffu, (meta & 0x100u) != 0u);
+            // epilogue operands requested now, consumed after the force loop
+            float2 v = make_float2(0.0f, 0.0f), rb = make_float2(0.0f, 0.0f);
+            if (live && rc.nsteps > 0) { v = V[i]; rb = a.Rb[i]; }
+            float Fx = 0.0f, Fy = 0.0f, pe = 0.0f, ke = 0.0f;
+            const int ii = live ? i : 0;
+            // the warp's three neighbour windows -> shared memory (coalesced), then LDS gathers
+            const int wid = i >> 5;
+            const int4 p0 = (wid * 32 < a.N) ? a.wplan[2 * wid] : make_int4(0, 0, 0, 0);
+            const bool staged = p0.w != 0;
+            float2* win = s_win[tid >> 5];
+            if (staged) {
+                const int4 p1 = a.wplan[2 * wid + 1];
+                const int lane = tid & 31;
+                __syncwarp();                                   // previous chunk's readers are done
+#pragma unroll
+                for (int j = 0; j < CL_WIN; j += 32) {
+                    if (j + lane < p1.x) win[j + lane] = R[p0.x + j + lane];
+                    if (j + lane < p1.y) win[CL_WIN + j + lane] = R[p0.y + j + lane];
+                    if (j + lane < p1.z) win[2 * CL_WIN + j + lane] = R[p0.z + j + lane];
+                }
+                __syncwarp();
+                if (want_pe) list_force<true,  false>(a, win, ii, n, ri, Fx, Fy, pe);
+                else         list_force<false, false>(a, win, ii, n, ri, Fx, Fy, pe);
+            } else if (want_pe) {
+                if (wedge) list_force<true, true >(a, R, ii, n, ri, Fx, Fy, pe);
+                else       list_force<true, false>(a, R, ii, n, ri, Fx, Fy, pe);
+            } else {
+                if (wedge) list_force<false, true >(a, R, ii, n, ri, Fx, Fy, pe);
+                else       list_force<false, false>(a, R, ii, n, ri, Fx, Fy, pe);
+            }
+            if (live) {
+                if (kick1) { v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt); }            // MD:74
+                if (want_ke) ke = v.x * v.x + v.y * v.y;
+                const int o = (sample || (final && !thermo)) ? og[i] : 0;
+                if (sample) rc.traj[(size_t)(s / rc.sample_every) * a.N + o] = ri;              // MD:93-100
+                if (thermo) {
+                    V[i] = v;
+                    a.Fs[i] = make_float2(Fx, Fy);
+                } else if (final) {
+                    if (a.R_out) a.R_out[o] = ri;
+                    if (a.V_out) a.V_out[o] = v;
+                    if (a.F_out) a.F_out[o] = make_float2(Fx, Fy);
+                } else {
+                    v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt);                         // MD:70
+                    V[i] = v;
+                    const float2 rn = make_float2(drift(ri.x, v.x, a.dt, a.pc.box),               // MD:71-72
+                                                  drift(ri.y, v.y, a.dt, a.pc.box));
+                    Rnext[i] = rn;
+                    const float ddx = min_image(__fsub_rn(rn.x, rb.x), a.pc.box, a.pc.timg);
+                    const float ddy = min_image(__fsub_rn(rn.y, rb.y), a.pc.box, a.pc.timg);
+                    moved |= (ddx * ddx + ddy * ddy > a.half_skin2);
+                }
+            }
+            // per-chunk energy partials (fixed reduction tree), summed in chunk order after the barrier
+            if (want_pe) {
+                const float t = block_sum<CL_THREADS>(pe, sred);
+                if (tid == 0) __stcg(&a.pe_part[par * a.nchunks + ch], t);
+            }
+            if (want_ke) {
+                const float t = block_sum<CL_THREADS>(ke, sred);
+                if (tid == 0) __stcg(&a.ke_part[par * a.nchunks + ch], t);
+            }
         }
-        if (fl.thermo) {
+        if (thermo) {
             CL_BARRIER();
-            const double ke2 = block_sum_array(a.ke_part + par * a.maxunits, ctx.nunits, sdbl);
+            const double ke2 = block_sum_array(a.ke_part + par * a.nchunks, a.nchunks, sdbl);
             if (tid == 0) s_lambda = sqrtf(rc.thermo_kT / ((float)(0.5 * ke2) / (float)a.N));
             __syncthreads();
             const float lam = s_lambda;
-            const float* X = a.X[ctx.pr];
-            const float* Y = a.Y[ctx.pr];
-            float* Xn = a.X[ctx.pr ^ 1];
-            float* Yn = a.Y[ctx.pr ^ 1];
-            float2* V = a.V[ctx.pv];
-            const int* og = a.orig[ctx.pv];
-            for (int i = gtid; i < ctx.ntot; i += gsz) {
-                const int o = og[i];
-                if (o < 0) { if (!fl.final) { Xn[i] = X[i]; Yn[i] = Y[i]; } continue; }   // pad stays put
-                const float rx = X[i], ry = Y[i];
+            for (int i = gtid; i < a.N; i += gsz) {
+                const float2 ri = R[i];
                 const float2 F = a.Fs[i];
                 float2 v = V[i];
                 v.x *= lam; v.y *= lam;
-                if (fl.final) {
-                    if (a.R_out) a.R_out[o] = make_float2(rx, ry);
+                if (final) {
+                    const int o = og[i];
+                    if (a.R_out) a.R_out[o] = ri;
                     if (a.V_out) a.V_out[o] = v;
                     if (a.F_out) a.F_out[o] = F;
                 } else {
                     v.x = kick(v.x, F.x, a.dt); v.y = kick(v.y, F.y, a.dt);
                     V[i] = v;
-                    const float xn = drift(rx, v.x, a.dt, a.pc.box), yn = drift(ry, v.y, a.dt, a.pc.box);
-                    Xn[i] = xn; Yn[i] = yn;
+                    const float2 rn = make_float2(drift(ri.x, v.x, a.dt, a.pc.box),
+                                                  drift(ri.y, v.y, a.dt, a.pc.box));
+                    Rnext[i] = rn;
                     const float2 rb = a.Rb[i];
-                    const float ddx = min_image(__fsub_rn(xn, rb.x), a.pc.box, a.pc.timg);
-                    const float ddy = min_image(__fsub_rn(yn, rb.y), a.pc.box, a.pc.timg);
+                    const float ddx = min_image(__fsub_rn(rn.x, rb.x), a.pc.box, a.pc.timg);
+                    const float ddy = min_image(__fsub_rn(rn.y, rb.y), a.pc.box, a.pc.timg);
                     moved |= (ddx * ddx + ddy * ddy > a.half_skin2);
                 }
             }
@@ -909,17 +598,17 @@ cells_persistent_kernel(const CellsArgs a) {
         // a particle left the skin/2 ball: ask for a rebuild before the next force evaluation.
         // The flag carries the step stamp, so it never needs clearing (no reset race).
         if (__syncthreads_or(moved) && tid == 0) __stcg(a.state + ST_FLAG, (int)(s + 2));
-        if (!fl.final) ctx.pr ^= 1;
+        if (!final) ctx.pr ^= 1;
         CL_PROF(0);
         CL_BARRIER();
         CL_PROF(1);
 
         if (blockIdx.x == 0 && want_pe) {
-            const double pe2 = block_sum_array(a.pe_part + par * a.maxunits, ctx.nunits, sdbl);
+            const double pe2 = block_sum_array(a.pe_part + par * a.nchunks, a.nchunks, sdbl);
             double ke2 = 0.0;
-            if (fl.want_e) ke2 = block_sum_array(a.ke_part + par * a.maxunits, ctx.nunits, sdbl);
+            if (want_e) ke2 = block_sum_array(a.ke_part + par * a.nchunks, a.nchunks, sdbl);
             if (tid == 0) {
-                if (fl.want_e) {
+                if (want_e) {
                     float* o = rc.ke_pe + 2 * (s / rc.energy_every);
                     o[0] = (float)(0.5 * ke2);
                     o[1] = (float)(0.5 * pe2);
@@ -929,9 +618,7 @@ cells_persistent_kernel(const CellsArgs a) {
             }
         }
     }
-    if (gtid == 0) {
-        a.state[ST_PR] = ctx.pr; a.state[ST_PV] = ctx.pv; a.state[ST_NTOT] = ctx.ntot;
-    }
+    if (gtid == 0) { a.state[ST_PR] = ctx.pr; a.state[ST_PV] = ctx.pv; }
     if (ctx.pt && tid == 0)
         for (int k = 0; k < 11; ++k) a.prof[blockIdx.x * 12 + k] = s_pt[k];
 }
@@ -951,18 +638,15 @@ __global__ void cell_assign_kernel(const float2* __restrict__ R, int N, int nrow
 
 // ----------------------------------------------------------------------------------------------------
 struct Cells {
-    int G = 0, nrows = 0, nbx = 0, ncells = 0, Nalloc = 0;
+    int G = 0, nrows = 0, nbx = 0, ncells = 0, Nalloc = 0, nchunks = 0;
     float inv_hy = 0, inv_wx = 0, hy = 0, wx = 0, rlist = 0;
-    float *X[2] = {nullptr, nullptr}, *Y[2] = {nullptr, nullptr};
-    float2 *V[2] = {nullptr, nullptr}, *Rb = nullptr, *Fs = nullptr;
+    float2 *R[2] = {nullptr, nullptr}, *V[2] = {nullptr, nullptr}, *Rb = nullptr, *Fs = nullptr;
     int *orig[2] = {nullptr, nullptr};
-    int *key = nullptr, *rank = nullptr, *tmp = nullptr, *cell_count = nullptr, *cell_start = nullptr,
-        *row_tot = nullptr, *sched = nullptr;
-    int2* unit_tab = nullptr;
-    UnitPlan* plans = nullptr;
-    uint2* pranges = nullptr;
-    int maxunits = 0;
-    size_t smem = 0;
+    int *key = nullptr, *rank = nullptr, *tmpk = nullptr, *tmpo = nullptr, *tmpc = nullptr,
+        *cell_count = nullptr, *cell_start = nullptr, *row_tot = nullptr;
+    unsigned* meta = nullptr;
+    uint2* ent = nullptr;
+    int4* wplan = nullptr;
     float *pe_part = nullptr, *ke_part = nullptr;
     int* state = nullptr;
     unsigned* bar = nullptr;
@@ -992,23 +676,20 @@ int cells_create(ljmd_handle* h) {
     cl->wx = h->p.box / (float)cl->nbx;
     cl->inv_hy = (float)cl->nrows / h->p.box;
     cl->inv_wx = (float)cl->nbx / h->p.box;
-    cl->Nalloc = (int)(((N + 3 * (long long)cl->nrows + 63) / 64) * 64 + 64);
+    cl->Nalloc = (int)(((N + 63) / 64) * 64);
+    cl->nchunks = (int)((N + CL_THREADS - 1) / CL_THREADS);
 
-    cl->maxunits = (int)(N / CL_UNIT + cl->nrows + 2);
-    cl->smem = sizeof(Stage) * CL_NST * CL_WARPS;
-    LJ_CUDA(cudaFuncSetAttribute(cells_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl->smem));
     int per_sm = 0;
-    LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cells_persistent_kernel, CL_THREADS, cl->smem));
+    LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cells_persistent_kernel, CL_THREADS, 0));
     if (per_sm < 1) { set_error("cell-list kernel does not fit on an SM"); return LJMD_E_STATE; }
     if (const char* e = getenv("LJMD_CELLS_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));
     long long g = (long long)per_sm * h->num_sms;
-    g = std::min<long long>(g, std::max<long long>(1, (N + CL_UNIT * CL_WARPS - 1) / (CL_UNIT * CL_WARPS)));
+    g = std::min<long long>(g, std::max<long long>(1, cl->nchunks));
     cl->G = (int)g;
 
     const size_t na = (size_t)cl->Nalloc;
     for (int k = 0; k < 2; ++k) {
-        LJ_CUDA(cudaMalloc(&cl->X[k], sizeof(float) * na));
-        LJ_CUDA(cudaMalloc(&cl->Y[k], sizeof(float) * na));
+        LJ_CUDA(cudaMalloc(&cl->R[k], sizeof(float2) * na));
         LJ_CUDA(cudaMalloc(&cl->V[k], sizeof(float2) * na));
         LJ_CUDA(cudaMalloc(&cl->orig[k], sizeof(int) * na));
     }
@@ -1016,19 +697,18 @@ int cells_create(ljmd_handle* h) {
     LJ_CUDA(cudaMalloc(&cl->Fs, sizeof(float2) * na));
     LJ_CUDA(cudaMalloc(&cl->key, sizeof(int) * na));
     LJ_CUDA(cudaMalloc(&cl->rank, sizeof(int) * na));
-    LJ_CUDA(cudaMalloc(&cl->tmp, sizeof(int) * na));
+    LJ_CUDA(cudaMalloc(&cl->tmpk, sizeof(int) * na));
+    LJ_CUDA(cudaMalloc(&cl->tmpo, sizeof(int) * na));
+    LJ_CUDA(cudaMalloc(&cl->tmpc, sizeof(int) * na));
+    LJ_CUDA(cudaMalloc(&cl->meta, sizeof(unsigned) * na));
+    LJ_CUDA(cudaMalloc(&cl->ent, sizeof(uint2) * na * CL_E));
+    LJ_CUDA(cudaMalloc(&cl->wplan, sizeof(int4) * 2 * (na / 32 + 1)));
     LJ_CUDA(cudaMalloc(&cl->cell_count, sizeof(int) * (size_t)cl->ncells));
     LJ_CUDA(cudaMemset(cl->cell_count, 0, sizeof(int) * (size_t)cl->ncells));
-    LJ_CUDA(cudaMalloc(&cl->cell_start, sizeof(int) * ((size_t)cl->ncells + 1 + 8)));   // + bulk-copy round-up
-    LJ_CUDA(cudaMemset(cl->cell_start, 0, sizeof(int) * ((size_t)cl->ncells + 1 + 8)));
+    LJ_CUDA(cudaMalloc(&cl->cell_start, sizeof(int) * ((size_t)cl->ncells + 1)));
     LJ_CUDA(cudaMalloc(&cl->row_tot, sizeof(int) * (size_t)cl->nrows));
-    LJ_CUDA(cudaMalloc(&cl->unit_tab, sizeof(int2) * (size_t)cl->maxunits));
-    LJ_CUDA(cudaMalloc(&cl->plans, sizeof(UnitPlan) * (size_t)cl->maxunits));
-    LJ_CUDA(cudaMalloc(&cl->sched, sizeof(int) * 2));
-    LJ_CUDA(cudaMalloc(&cl->pranges, sizeof(uint2) * (na / 2 + 64)));
-    LJ_CUDA(cudaMemset(cl->pranges, 0, sizeof(uint2) * (na / 2 + 64)));
-    LJ_CUDA(cudaMalloc(&cl->pe_part, sizeof(float) * 2 * cl->maxunits));
-    LJ_CUDA(cudaMalloc(&cl->ke_part, sizeof(float) * 2 * cl->maxunits));
+    LJ_CUDA(cudaMalloc(&cl->pe_part, sizeof(float) * 2 * cl->nchunks));
+    LJ_CUDA(cudaMalloc(&cl->ke_part, sizeof(float) * 2 * cl->nchunks));
     LJ_CUDA(cudaMalloc(&cl->state, sizeof(int) * ST_WORDS));
     LJ_CUDA(cudaMemset(cl->state, 0, sizeof(int) * ST_WORDS));
     LJ_CUDA(cudaMalloc(&cl->bar, sizeof(unsigned)));
@@ -1039,10 +719,10 @@ int cells_create(ljmd_handle* h) {
 void cells_destroy(ljmd_handle* h) {
     Cells* cl = h->cells;
     if (!cl) return;
-    for (int k = 0; k < 2; ++k) { cudaFree(cl->X[k]); cudaFree(cl->Y[k]); cudaFree(cl->V[k]); cudaFree(cl->orig[k]); }
-    cudaFree(cl->Rb); cudaFree(cl->Fs); cudaFree(cl->key); cudaFree(cl->rank); cudaFree(cl->tmp);
+    for (int k = 0; k < 2; ++k) { cudaFree(cl->R[k]); cudaFree(cl->V[k]); cudaFree(cl->orig[k]); }
+    cudaFree(cl->Rb); cudaFree(cl->Fs); cudaFree(cl->key); cudaFree(cl->rank);
+    cudaFree(cl->tmpk); cudaFree(cl->tmpo); cudaFree(cl->tmpc); cudaFree(cl->meta); cudaFree(cl->ent); cudaFree(cl->wplan);
     cudaFree(cl->cell_count); cudaFree(cl->cell_start); cudaFree(cl->row_tot);
-    cudaFree(cl->unit_tab); cudaFree(cl->plans); cudaFree(cl->pranges); cudaFree(cl->sched);
     cudaFree(cl->pe_part); cudaFree(cl->ke_part);
     cudaFree(cl->state); cudaFree(cl->bar); cudaFree(cl->prof);
     delete cl;
@@ -1052,17 +732,17 @@ void cells_destroy(ljmd_handle* h) {
 static void fill_args(ljmd_handle* h, CellsArgs& a) {
     Cells* cl = h->cells;
     a.pc = h->pc;
-    a.N = (int)h->p.N; a.Nalloc = cl->Nalloc; a.G = cl->G;
+    a.N = (int)h->p.N; a.Nalloc = cl->Nalloc; a.G = cl->G; a.nchunks = cl->nchunks;
     a.nrows = cl->nrows; a.nbx = cl->nbx; a.ncells = cl->ncells;
     a.inv_hy = cl->inv_hy; a.inv_wx = cl->inv_wx;
+    a.rlist2 = cl->rlist * cl->rlist;
     a.half_skin2 = (0.5f * h->p.skin) * (0.5f * h->p.skin);
     a.dt = h->p.dt;
-    for (int k = 0; k < 2; ++k) { a.X[k] = cl->X[k]; a.Y[k] = cl->Y[k]; a.V[k] = cl->V[k]; a.orig[k] = cl->orig[k]; }
+    for (int k = 0; k < 2; ++k) { a.R[k] = cl->R[k]; a.V[k] = cl->V[k]; a.orig[k] = cl->orig[k]; }
     a.Rb = cl->Rb; a.Fs = cl->Fs;
-    a.key = cl->key; a.rank = cl->rank; a.tmp = cl->tmp;
+    a.key = cl->key; a.rank = cl->rank; a.tmpk = cl->tmpk; a.tmpo = cl->tmpo; a.tmpc = cl->tmpc;
     a.cell_count = cl->cell_count; a.cell_start = cl->cell_start; a.row_tot = cl->row_tot;
-    a.sched = cl->sched;
-    a.unit_tab = cl->unit_tab; a.plans = cl->plans; a.pranges = cl->pranges; a.maxunits = cl->maxunits;
+    a.meta = cl->meta; a.ent = cl->ent; a.wplan = cl->wplan;
     a.pe_part = cl->pe_part; a.ke_part = cl->ke_part;
     a.state = cl->state; a.bar = cl->bar; a.prof = cl->prof;
 }
@@ -1070,10 +750,9 @@ static void fill_args(ljmd_handle* h, CellsArgs& a) {
 static int launch(ljmd_handle* h, CellsArgs& a) {
     Cells* cl = h->cells;
     LJ_CUDA(cudaMemsetAsync(cl->bar, 0, sizeof(unsigned), h->stream));
-    LJ_CUDA(cudaMemsetAsync(cl->sched, 0, sizeof(int) * 2, h->stream));
     void* args[] = {(void*)&a};
     LJ_CUDA(cudaLaunchCooperativeKernel((void*)cells_persistent_kernel, dim3(cl->G), dim3(CL_THREADS),
-                                        args, cl->smem, h->stream));
+                                        args, 0, h->stream));
     h->launches++;
     return 0;
 }
@@ -1087,7 +766,7 @@ int cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_
         LJ_CUDA(cudaMemsetAsync(rc.traj, 0, sizeof(float2) * N * rc.S, st));      // MD:89
     // fresh call: parities 0, rebuild counter 0, flag 0 (the error word is sticky)
     LJ_CUDA(cudaMemsetAsync(cl->state, 0, sizeof(int) * 3, st));
-    LJ_CUDA(cudaMemsetAsync(cl->state + ST_FLAG, 0, sizeof(int) * 3, st));
+    LJ_CUDA(cudaMemsetAsync(cl->state + ST_FLAG, 0, sizeof(int), st));
     CellsArgs a{};
     fill_args(h, a);
     a.R_in = R_in; a.V_in = V_in;
@@ -1113,7 +792,7 @@ int cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_
         std::vector<long long> pv(12 * cl->G);
         LJ_CUDA(cudaMemcpy(pv.data(), cl->prof, sizeof(long long) * pv.size(), cudaMemcpyDeviceToHost));
         const char* nm[8] = {"force+integrate", "step barrier", "B1 bin+hist", "B2 row totals",
-                             "B3 scan", "B4 scatter", "B5 order+gather", "B6 copy plans"};
+                             "B3 scan", "B4 scatter", "B5 order+gather", "B6 list build"};
         for (int k = 0; k < 8; ++k) {
             double mean = 0, mx = 0;
             for (int c = 0; c < cl->G; ++c) { mean += pv[c * 12 + k]; mx = std::max<double>(mx, (double)pv[c * 12 + k]); }
@@ -1151,7 +830,7 @@ int cells_neighbor_count(ljmd_handle* h, const float2* R, float radius, int* nbr
         return LJMD_E_INVALID;
     }
     LJ_CUDA(cudaMemsetAsync(cl->state, 0, sizeof(int) * 3, h->stream));
-    LJ_CUDA(cudaMemsetAsync(cl->state + ST_FLAG, 0, sizeof(int) * 3, h->stream));
+    LJ_CUDA(cudaMemsetAsync(cl->state + ST_FLAG, 0, sizeof(int), h->stream));
     CellsArgs a{};
     fill_args(h, a);
     a.R_in = R; a.V_in = nullptr;
@@ -1175,6 +854,10 @@ int cells_check_error(ljmd_handle* h) {
     if (!cl) return 0;
     int e = 0;
     LJ_CUDA(cudaMemcpy(&e, cl->state + ST_ERR, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e & CERR_LIST_OVERFLOW) {
+        set_error("cell-list: a particle needs more than %d list entries (too dense for rc+skin)", CL_E);
+        return LJMD_E_STATE;
+    }
     if (e) { set_error("cell-list persistent kernel: grid barrier timed out (flag %d)", e); return LJMD_E_STATE; }
     return 0;
 }
