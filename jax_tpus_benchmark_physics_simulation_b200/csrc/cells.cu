@@ -26,7 +26,11 @@
 //   wplan    int4 x2 per warp of 32 slots: the three contiguous slot windows that hold every
 //                    neighbour of the warp's particles.  The per-step pass copies them to shared
 //                    memory with coalesced loads, so the gathers of the pair loop are LDS, not
-//                    scattered global loads; entries of such a warp are window-relative.
+//                    scattered global loads.
+//   nb4      uint32  for such a warp the list is stored EXPANDED: one byte per neighbour = its index
+//                    in the staged windows (<= 252 slots), four per word, ELL layout, padded with a
+//                    sentinel index to the warp's longest list: decode is a shift, there is no
+//                    per-lane trip count.  (first slot, mask) entries remain for the other warps.
 //   cell_start int32 prefix-sum cell index over nrows*nbx cells (+1)
 //
 // One PERSISTENT cooperative kernel runs a whole ljmd_run(): per step ONE pass over the state
@@ -46,7 +50,15 @@ namespace {
 constexpr int CL_THREADS   = 512;
 constexpr int CL_K         = 4;     // bins per (rc + skin)
 constexpr int CL_E         = 8;     // list entries per particle (3 when every range fits 32 slots)
-constexpr int CL_WIN       = 96;    // staged window capacity per stencil row and warp (slots)
+constexpr int CL_WIN       = 84;    // staged window capacity per stencil row and warp (slots):
+                                    // 3 * CL_WIN = 252 slots fit a one-byte neighbour index
+constexpr int CL_WSLOTS    = 256;   // a warp's staging buffer: three windows + 4 sentinel slots
+constexpr int CL_DUMMY     = 255;   // byte index of a sentinel slot (pads the byte lists)
+constexpr int CL_NW        = 16;    // byte-list words per particle (64 neighbours)
+constexpr int CL_NWPRE     = 6;     // words requested before the loop (24 neighbours)
+constexpr int CL_BROW      = 4 * CL_NW + 4;   // a lane's byte row while a list is built (17 words:
+                                              // rows of different lanes start in different banks)
+constexpr int CL_WARP_SMEM = CL_WSLOTS * 8 + 32 * CL_BROW;            // bytes per warp
 constexpr int CL_WARPS     = CL_THREADS / 32;
 constexpr int CL_ORDER_MAX = 64;    // cells denser than this keep arrival order (see B5)
 
@@ -66,8 +78,10 @@ struct CellsArgs {
     int *key, *rank, *tmpk, *tmpo, *tmpc, *cell_count, *cell_start, *row_tot;
     unsigned* meta;
     uint2*    ent;
+    unsigned* nb4;                  // byte lists of staged warps, ELL nb4[w * Nalloc + i]
     int4*     wplan;                // per warp of 32 slots: 2 x int4 (window starts / lengths, flag)
     float  *pe_part, *ke_part;      // [2*nchunks] per-chunk partials (by step parity)
+    int*      sched;                // [2] chunk counters (by step parity)
     int*      state;                // ST_* words
     unsigned* bar;
     const float2* R_in;
@@ -149,7 +163,8 @@ struct Ctx {
 
 // ---- rebuild: counting sort by cell, deterministic in-cell order, bitmask Verlet list --------------
 // lim2: list radius squared (rc + skin for a run, the caller's radius in count mode)
-__device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float lim2) {
+__device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* win /* this warp's CL_WSLOTS slots */,
+                              unsigned char* sbytes /* this warp's 32 byte rows */, float lim2) {
     const int tid = threadIdx.x, gtid = blockIdx.x * CL_THREADS + tid, gsz = a.G * CL_THREADS;
     const float2* __restrict__ Rc = a.R[ctx.pr];
     const int* __restrict__ orig_old = a.orig[ctx.pv];
@@ -300,46 +315,100 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float li
                 a.wplan[2 * (i0 >> 5)]     = make_int4(ws[0], ws[1], ws[2], staged ? 1 : 0);
                 a.wplan[2 * (i0 >> 5) + 1] = make_int4(wn[0], wn[1], wn[2], 0);
             }
-            if (!live) continue;
-            const int lo = b - CL_K, hi = b + CL_K;
             int n = 0, cnt = 0;
-            for (int k = 0; k < 3; ++k) {
-                int rr = r + k - 1;
-                rr += (rr < 0) ? a.nrows : 0;
-                rr -= (rr >= a.nrows) ? a.nrows : 0;
-                const int* __restrict__ csr = cs + rr * a.nbx;
-                for (int piece = 0; piece < 3; ++piece) {
-                    int bl, bh;
-                    if (piece == 0)      { bl = max(lo, 0); bh = min(hi, a.nbx - 1); }
-                    else if (piece == 1) { if (lo >= 0) continue; bl = lo + a.nbx; bh = a.nbx - 1; }
-                    else                 { if (hi < a.nbx) continue; bl = 0; bh = hi - a.nbx; }
-                    const int s = csr[bl], e = csr[bh + 1];
-                    for (int c0 = s; c0 < e; c0 += 32) {
-                        const int cnum = min(32, e - c0);
-                        unsigned mask = 0u;
-                        for (int t0 = 0; t0 < cnum; t0 += 4) {          // four position loads in flight
-                            float2 rj[4];
+            if (staged) {
+                // fast path: the warp's windows in shared memory (coalesced copy), every lane scans its
+                // three ranges there, two candidates per step on the packed pipe; no minimum image
+                // (identity this far from the box edge)
+                __syncwarp();
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) rj[u] = R[c0 + min(t0 + u, cnum - 1)];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const float dx = min_image(__fsub_rn(ri.x, rj[u].x), pc.box, pc.timg);
-                                const float dy = min_image(__fsub_rn(ri.y, rj[u].y), pc.box, pc.timg);
-                                const float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-                                if (t0 + u < cnum && r2 < lim2 && c0 + t0 + u != i) mask |= 1u << (t0 + u);
-                            }
+                for (int j = 0; j < CL_WIN; j += 32) {
+                    if (j + lane < wn[0]) win[j + lane] = R[ws[0] + j + lane];
+                    if (j + lane < wn[1]) win[CL_WIN + j + lane] = R[ws[1] + j + lane];
+                    if (j + lane < wn[2]) win[2 * CL_WIN + j + lane] = R[ws[2] + j + lane];
+                }
+                __syncwarp();
+                // neighbour indices are appended branch-free to this lane's byte row in shared
+                // memory (a rejected candidate is overwritten by the next one), then written out as
+                // coalesced words
+                unsigned char* myb = sbytes + lane * CL_BROW;
+                int nn = 0;                                             // neighbours appended so far
+                if (live) {
+                    const float2 nri = make_float2(-ri.x, -ri.y);
+#pragma unroll 1
+                    for (int k = 0; k < 3; ++k) {
+                        const int s = cs[(r + k - 1) * a.nbx + b - CL_K] - ws[k];
+                        const int e = cs[(r + k - 1) * a.nbx + b + CL_K + 1] - ws[k];
+                        const float2* __restrict__ w = win + k * CL_WIN;
+                        const int iself = (k == 1) ? i - ws[k] : -1;    // own slot (own row only)
+#pragma unroll 2
+                        for (int t = s; t < e; t += 2) {
+                            const float2 d0 = __fadd2_rn(w[t], nri);
+                            const float2 d1 = __fadd2_rn(w[min(t + 1, e - 1)], nri);
+                            const float2 q0 = __fmul2_rn(d0, d0), q1 = __fmul2_rn(d1, d1);
+                            const float r20 = __fadd_rn(q0.x, q0.y), r21 = __fadd_rn(q1.x, q1.y);
+                            const bool in0 = (r20 < lim2) & (t != iself);
+                            const bool in1 = (r21 < lim2) & (t + 1 < e) & (t + 1 != iself);
+                            myb[min(nn, 4 * CL_NW)] = (unsigned char)(k * CL_WIN + t);
+                            nn += in0 ? 1 : 0;
+                            myb[min(nn, 4 * CL_NW)] = (unsigned char)(k * CL_WIN + t + 1);
+                            nn += in1 ? 1 : 0;
                         }
-                        if (mask) {
-                            // staged warp: window-relative slot (the three windows are laid out back
-                            // to back, CL_WIN slots each); otherwise the absolute slot
-                            const unsigned first = staged ? (unsigned)(k * CL_WIN + c0 - ws[k]) : (unsigned)c0;
-                            if (a.mode == 0 && n < CL_E) a.ent[(size_t)n * a.Nalloc + i] = make_uint2(first, mask);
-                            ++n;
-                            cnt += __popc(mask);
+                    }
+                }
+                // pad to the warp's longest list with the sentinel index: the per-step loop needs no
+                // per-lane trip count
+                const int nw = (nn + 3) >> 2;
+                int nwmax = nw;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) nwmax = max(nwmax, __shfl_xor_sync(0xffffffffu, nwmax, o));
+                nwmax = min(nwmax, CL_NW);
+                if (live) {
+                    for (int q = min(nn, 4 * CL_NW); q < 4 * nwmax; ++q) myb[q] = (unsigned char)CL_DUMMY;
+                    if (nw > CL_NW) atomicOr(a.state + ST_ERR, CERR_LIST_OVERFLOW);
+                    const unsigned* myw = reinterpret_cast<const unsigned*>(myb);
+                    for (int u = 0; u < nwmax; ++u) a.nb4[(size_t)u * a.Nalloc + i] = myw[u];
+                }
+                if (lane == 0) a.wplan[2 * (i0 >> 5) + 1].w = nwmax;
+                n = 0;
+            } else if (live) {
+                const int lo = b - CL_K, hi = b + CL_K;
+                for (int k = 0; k < 3; ++k) {
+                    int rr = r + k - 1;
+                    rr += (rr < 0) ? a.nrows : 0;
+                    rr -= (rr >= a.nrows) ? a.nrows : 0;
+                    const int* __restrict__ csr = cs + rr * a.nbx;
+                    for (int piece = 0; piece < 3; ++piece) {
+                        int bl, bh;
+                        if (piece == 0)      { bl = max(lo, 0); bh = min(hi, a.nbx - 1); }
+                        else if (piece == 1) { if (lo >= 0) continue; bl = lo + a.nbx; bh = a.nbx - 1; }
+                        else                 { if (hi < a.nbx) continue; bl = 0; bh = hi - a.nbx; }
+                        const int s = csr[bl], e = csr[bh + 1];
+                        for (int c0 = s; c0 < e; c0 += 32) {
+                            const int cnum = min(32, e - c0);
+                            unsigned mask = 0u;
+                            for (int t0 = 0; t0 < cnum; t0 += 4) {          // four position loads in flight
+                                float2 rj[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) rj[u] = R[c0 + min(t0 + u, cnum - 1)];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const float dx = min_image(__fsub_rn(ri.x, rj[u].x), pc.box, pc.timg);
+                                    const float dy = min_image(__fsub_rn(ri.y, rj[u].y), pc.box, pc.timg);
+                                    const float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                                    if (t0 + u < cnum && r2 < lim2 && c0 + t0 + u != i) mask |= 1u << (t0 + u);
+                                }
+                            }
+                            if (mask) {
+                                if (a.mode == 0 && n < CL_E) a.ent[(size_t)n * a.Nalloc + i] = make_uint2((unsigned)c0, mask);
+                                ++n;
+                                cnt += __popc(mask);
+                            }
                         }
                     }
                 }
             }
+            if (!live) continue;
             if (a.mode == 0) {
                 if (n > CL_E) atomicOr(a.state + ST_ERR, CERR_LIST_OVERFLOW);
                 a.meta[i] = (unsigned)min(n, CL_E) | (edge ? 0x100u : 0u);
@@ -425,6 +494,40 @@ __device__ __forceinline__ void list_force(const CellsArgs& a, const float2* R, 
     if (PE) pe = pe2.x + pe2.y;
 }
 
+// staged warps: the list is one byte per neighbour (index into the staged windows), four per word,
+// padded with the sentinel index to the warp's longest list (nw words, warp-uniform)
+template <bool PE>
+__device__ __forceinline__ void word_eval(const PairConsts& pc, const PairConsts2& c2, const float2* win,
+                                          unsigned word, float2 nri, float2& acc, float2& pe2) {
+    const float2 r0 = win[word & 0xffu], r1 = win[(word >> 8) & 0xffu];
+    const float2 r2 = win[(word >> 16) & 0xffu], r3 = win[word >> 24];
+    eval_two<PE, false>(pc, c2, nri, r0, r1, true, acc, pe2);
+    eval_two<PE, false>(pc, c2, nri, r2, r3, true, acc, pe2);
+}
+
+template <bool PE>
+__device__ __forceinline__ void bytes_force(const CellsArgs& a, const float2* win, int i, int nw, float2 ri,
+                                            float& Fx, float& Fy, float& pe) {
+    const PairConsts pc = a.pc;
+    const PairConsts2 c2 = make_pair_consts2(pc);
+    const unsigned* __restrict__ np = a.nb4 + i;
+    const size_t stride = (size_t)a.Nalloc;
+    unsigned w[CL_NWPRE];
+#pragma unroll
+    for (int u = 0; u < CL_NWPRE; ++u) w[u] = (u < nw) ? np[(size_t)u * stride] : 0xffffffffu;
+    const float2 nri = make_float2(-ri.x, -ri.y);
+    float2 acc = make_float2(0.0f, 0.0f), pe2 = acc;
+#pragma unroll
+    for (int u = 0; u < CL_NWPRE; ++u)
+        if (u < nw) word_eval<PE>(pc, c2, win, w[u], nri, acc, pe2);          // warp-uniform
+    for (int u = CL_NWPRE; u < nw; ++u) word_eval<PE>(pc, c2, win, np[(size_t)u * stride], nri, acc, pe2);
+    Fx = -acc.x;
+    Fy = -acc.y;
+    if (PE) pe = pe2.x + pe2.y;
+}
+
+extern __shared__ __align__(16) unsigned char cells_smem[];
+
 __global__ void __launch_bounds__(CL_THREADS, 2)
 cells_persistent_kernel(const CellsArgs a) {
     __shared__ int    sscan[CL_THREADS / 32 + 1];
@@ -432,7 +535,7 @@ cells_persistent_kernel(const CellsArgs a) {
     __shared__ double sdbl[CL_THREADS / 32];
     __shared__ float  s_lambda;
     __shared__ long long s_pt[12];
-    __shared__ float2 s_win[CL_WARPS][3 * CL_WIN];      // each warp's staged neighbour windows
+    __shared__ int    s_ch[2][2];                       // (current, next) chunk, double-buffered
     const int tid = threadIdx.x, gtid = blockIdx.x * CL_THREADS + tid, gsz = a.G * CL_THREADS;
     const RunCtl rc = a.rc;
     Ctx ctx;
@@ -441,6 +544,12 @@ cells_persistent_kernel(const CellsArgs a) {
     if (ctx.pt && tid == 0) { for (int k = 0; k < 11; ++k) s_pt[k] = 0; s_pt[11] = clock64(); }
     ctx.pr = a.state[ST_PR];
     ctx.pv = a.state[ST_PV];
+    // per warp: staged neighbour windows (+ sentinel slots) and the byte rows of the list build
+    float2* my_win = reinterpret_cast<float2*>(cells_smem + (size_t)(tid >> 5) * CL_WARP_SMEM);
+    unsigned char* my_bytes = cells_smem + (size_t)(tid >> 5) * CL_WARP_SMEM + CL_WSLOTS * 8;
+    // the sentinel slots behind the staged windows (never within rc of anything; never overwritten)
+    if ((tid & 31) >= 28) my_win[3 * CL_WIN + (tid & 3)] = make_float2(1.0e9f, 1.0e9f);
+    __syncthreads();
 
     if (a.s_begin < 0) {
         // load the caller's state (original order) and sort it
@@ -450,7 +559,7 @@ cells_persistent_kernel(const CellsArgs a) {
             a.orig[ctx.pv][i] = i;
         }
         CL_BARRIER();
-        cells_rebuild(a, ctx, sscan, (a.mode == 1) ? a.count_r2 : a.rlist2);
+        cells_rebuild(a, ctx, sscan, my_win, my_bytes, (a.mode == 1) ? a.count_r2 : a.rlist2);
         if (a.mode == 1) {
             const int* og = a.orig[ctx.pv];
             for (int i = gtid; i < a.N; i += gsz) a.count_out[og[i]] = a.key[i];
@@ -472,28 +581,38 @@ cells_persistent_kernel(const CellsArgs a) {
         const bool want_ke = want_e || thermo;
         // rebuild requested by the previous step's displacement test?
         if (s > a.s_begin || a.s_begin >= 0) {
-            if (__ldcg(a.state + ST_FLAG) == (int)(s + 1)) cells_rebuild(a, ctx, sscan, a.rlist2);
+            if (__ldcg(a.state + ST_FLAG) == (int)(s + 1)) cells_rebuild(a, ctx, sscan, my_win, my_bytes, a.rlist2);
         }
         const float2* __restrict__ R = a.R[ctx.pr];
         float2*       Rnext = a.R[ctx.pr ^ 1];
         float2*       V     = a.V[ctx.pv];
         const int*    og    = a.orig[ctx.pv];
 
+        // Chunks of CL_THREADS slots are handed out dynamically (one atomic per chunk, drawn two
+        // chunks ahead by thread 0): rows differ in density and edge warps are slower, a static
+        // split leaves CTAs idle at the barrier.  No result depends on which CTA ran a chunk.
+        if (gtid == 0) __stcg(&a.sched[par ^ 1], 0);     // the other parity's counter: idle this step
+        int c_cur = 0, c_nxt = 0;
+        if (tid == 0) { c_cur = atomicAdd(&a.sched[par], 1); c_nxt = atomicAdd(&a.sched[par], 1); }
         int moved = 0;
-        for (int ch = blockIdx.x; ch < a.nchunks; ch += a.G) {
+        for (int it = 0;; ++it) {
+            if (tid == 0) { s_ch[it & 1][0] = c_cur; s_ch[it & 1][1] = c_nxt; }
+            __syncthreads();
+            const int ch = s_ch[it & 1][0], chn = s_ch[it & 1][1];
+            if (ch >= a.nchunks) break;
+            if (tid == 0) { c_cur = c_nxt; c_nxt = atomicAdd(&a.sched[par], 1); }
             const int  i    = ch * CL_THREADS + tid;
             const bool live = i < a.N;
             // The pass streams ~70 bytes per particle and a warp has one particle per lane in flight:
             // without help the SM holds too few bytes in flight to cover the HBM latency.  Request the
             // NEXT chunk's operands now (L2 -> L1 prefetch); they arrive while this chunk is evaluated.
             {
-                const int inext = i + a.G * CL_THREADS;
+                const int inext = chn * CL_THREADS + tid;
                 if (inext < a.N) {
                     prefetch_l1(R + inext);
                     prefetch_l1(a.meta + inext);
-                    prefetch_l1(a.ent + inext);
-                    prefetch_l1(a.ent + (size_t)a.Nalloc + inext);
-                    prefetch_l1(a.ent + 2 * (size_t)a.Nalloc + inext);
+#pragma unroll
+                    for (int u = 0; u < CL_NWPRE; ++u) prefetch_l1(a.nb4 + (size_t)u * a.Nalloc + inext);
                     if (rc.nsteps > 0) { prefetch_l1(V + inext); prefetch_l1(a.Rb + inext); }
                     if ((tid & 31) == 0) prefetch_l1(a.wplan + 2 * (inext >> 5));
                 }
@@ -512,7 +631,7 @@ cells_persistent_kernel(const CellsArgs a) {
             const int wid = i >> 5;
             const int4 p0 = (wid * 32 < a.N) ? a.wplan[2 * wid] : make_int4(0, 0, 0, 0);
             const bool staged = p0.w != 0;
-            float2* win = s_win[tid >> 5];
+            float2* win = my_win;
             if (staged) {
                 const int4 p1 = a.wplan[2 * wid + 1];
                 const int lane = tid & 31;
@@ -524,8 +643,8 @@ cells_persistent_kernel(const CellsArgs a) {
                     if (j + lane < p1.z) win[2 * CL_WIN + j + lane] = R[p0.z + j + lane];
                 }
                 __syncwarp();
-                if (want_pe) list_force<true,  false>(a, win, ii, n, ri, Fx, Fy, pe);
-                else         list_force<false, false>(a, win, ii, n, ri, Fx, Fy, pe);
+                if (want_pe) bytes_force<true >(a, win, ii, p1.w, ri, Fx, Fy, pe);
+                else         bytes_force<false>(a, win, ii, p1.w, ri, Fx, Fy, pe);
             } else if (want_pe) {
                 if (wedge) list_force<true, true >(a, R, ii, n, ri, Fx, Fy, pe);
                 else       list_force<true, false>(a, R, ii, n, ri, Fx, Fy, pe);
@@ -646,9 +765,11 @@ struct Cells {
         *cell_count = nullptr, *cell_start = nullptr, *row_tot = nullptr;
     unsigned* meta = nullptr;
     uint2* ent = nullptr;
+    unsigned* nb4 = nullptr;
     int4* wplan = nullptr;
     float *pe_part = nullptr, *ke_part = nullptr;
     int* state = nullptr;
+    int* sched = nullptr;
     unsigned* bar = nullptr;
     long long* prof = nullptr;
 };
@@ -679,8 +800,10 @@ int cells_create(ljmd_handle* h) {
     cl->Nalloc = (int)(((N + 63) / 64) * 64);
     cl->nchunks = (int)((N + CL_THREADS - 1) / CL_THREADS);
 
+    const size_t smem = (size_t)CL_WARPS * CL_WARP_SMEM;
+    LJ_CUDA(cudaFuncSetAttribute(cells_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cells_persistent_kernel, CL_THREADS, 0));
+    LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cells_persistent_kernel, CL_THREADS, smem));
     if (per_sm < 1) { set_error("cell-list kernel does not fit on an SM"); return LJMD_E_STATE; }
     if (const char* e = getenv("LJMD_CELLS_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));
     long long g = (long long)per_sm * h->num_sms;
@@ -703,6 +826,7 @@ int cells_create(ljmd_handle* h) {
     LJ_CUDA(cudaMalloc(&cl->meta, sizeof(unsigned) * na));
     LJ_CUDA(cudaMalloc(&cl->ent, sizeof(uint2) * na * CL_E));
     LJ_CUDA(cudaMalloc(&cl->wplan, sizeof(int4) * 2 * (na / 32 + 1)));
+    LJ_CUDA(cudaMalloc(&cl->nb4, sizeof(unsigned) * na * CL_NW));
     LJ_CUDA(cudaMalloc(&cl->cell_count, sizeof(int) * (size_t)cl->ncells));
     LJ_CUDA(cudaMemset(cl->cell_count, 0, sizeof(int) * (size_t)cl->ncells));
     LJ_CUDA(cudaMalloc(&cl->cell_start, sizeof(int) * ((size_t)cl->ncells + 1)));
@@ -712,6 +836,7 @@ int cells_create(ljmd_handle* h) {
     LJ_CUDA(cudaMalloc(&cl->state, sizeof(int) * ST_WORDS));
     LJ_CUDA(cudaMemset(cl->state, 0, sizeof(int) * ST_WORDS));
     LJ_CUDA(cudaMalloc(&cl->bar, sizeof(unsigned)));
+    LJ_CUDA(cudaMalloc(&cl->sched, sizeof(int) * 2));
     if (getenv("LJMD_CELLS_PROF")) LJ_CUDA(cudaMalloc(&cl->prof, sizeof(long long) * 12 * cl->G));
     return 0;
 }
@@ -721,10 +846,10 @@ void cells_destroy(ljmd_handle* h) {
     if (!cl) return;
     for (int k = 0; k < 2; ++k) { cudaFree(cl->R[k]); cudaFree(cl->V[k]); cudaFree(cl->orig[k]); }
     cudaFree(cl->Rb); cudaFree(cl->Fs); cudaFree(cl->key); cudaFree(cl->rank);
-    cudaFree(cl->tmpk); cudaFree(cl->tmpo); cudaFree(cl->tmpc); cudaFree(cl->meta); cudaFree(cl->ent); cudaFree(cl->wplan);
+    cudaFree(cl->tmpk); cudaFree(cl->tmpo); cudaFree(cl->tmpc); cudaFree(cl->meta); cudaFree(cl->ent); cudaFree(cl->wplan); cudaFree(cl->nb4);
     cudaFree(cl->cell_count); cudaFree(cl->cell_start); cudaFree(cl->row_tot);
     cudaFree(cl->pe_part); cudaFree(cl->ke_part);
-    cudaFree(cl->state); cudaFree(cl->bar); cudaFree(cl->prof);
+    cudaFree(cl->state); cudaFree(cl->bar); cudaFree(cl->prof); cudaFree(cl->sched);
     delete cl;
     h->cells = nullptr;
 }
@@ -742,17 +867,18 @@ static void fill_args(ljmd_handle* h, CellsArgs& a) {
     a.Rb = cl->Rb; a.Fs = cl->Fs;
     a.key = cl->key; a.rank = cl->rank; a.tmpk = cl->tmpk; a.tmpo = cl->tmpo; a.tmpc = cl->tmpc;
     a.cell_count = cl->cell_count; a.cell_start = cl->cell_start; a.row_tot = cl->row_tot;
-    a.meta = cl->meta; a.ent = cl->ent; a.wplan = cl->wplan;
+    a.meta = cl->meta; a.ent = cl->ent; a.wplan = cl->wplan; a.nb4 = cl->nb4;
     a.pe_part = cl->pe_part; a.ke_part = cl->ke_part;
-    a.state = cl->state; a.bar = cl->bar; a.prof = cl->prof;
+    a.state = cl->state; a.bar = cl->bar; a.prof = cl->prof; a.sched = cl->sched;
 }
 
 static int launch(ljmd_handle* h, CellsArgs& a) {
     Cells* cl = h->cells;
     LJ_CUDA(cudaMemsetAsync(cl->bar, 0, sizeof(unsigned), h->stream));
+    LJ_CUDA(cudaMemsetAsync(cl->sched, 0, sizeof(int) * 2, h->stream));
     void* args[] = {(void*)&a};
     LJ_CUDA(cudaLaunchCooperativeKernel((void*)cells_persistent_kernel, dim3(cl->G), dim3(CL_THREADS),
-                                        args, 0, h->stream));
+                                        args, (size_t)CL_WARPS * CL_WARP_SMEM, h->stream));
     h->launches++;
     return 0;
 }
