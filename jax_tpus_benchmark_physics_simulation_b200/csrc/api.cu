@@ -82,11 +82,6 @@ int create_common(ljmd_t** out, const ljmd_params* p, int rank, int nranks, cons
         return rcode;
     }
     if (nranks > 1) {
-        if (path != LJMD_PATH_ALLPAIRS) {
-            set_error("multi-GPU: only the all-pairs path is sharded in this build (cell-list slabs: see DESIGN.md)");
-            ljmd_destroy(h);
-            return LJMD_E_UNSUPPORTED;
-        }
         rcode = dist_init(h, nccl_uid);
         if (rcode) { ljmd_destroy(h); return rcode; }
     }

@@ -62,13 +62,28 @@ constexpr int CL_WARP_SMEM = CL_WSLOTS * 8 + 32 * CL_BROW;            // bytes p
 constexpr int CL_WARPS     = CL_THREADS / 32;
 constexpr int CL_ORDER_MAX = 64;    // cells denser than this keep arrival order (see B5)
 
-enum { ST_PR = 0, ST_PV = 1, ST_REBUILDS = 2, ST_ERR = 3, ST_FLAG = 4, ST_WORDS = 8 };
-enum { CERR_BARRIER = 1, CERR_LIST_OVERFLOW = 2 };
+enum { ST_PR = 0, ST_PV = 1, ST_REBUILDS = 2, ST_ERR = 3, ST_FLAG = 4, ST_NHELD = 5, ST_OWN_S = 6,
+       ST_OWN_E = 7, ST_LOADCNT = 8, ST_XEPOCH = 9, ST_LMOVED = 10, ST_WORDS = 12 };
+enum { CERR_BARRIER = 1, CERR_LIST_OVERFLOW = 2, CERR_PEER = 4, CERR_CAPACITY = 8 };
+// mailbox words a neighbour writes (slab decomposition)
+enum { MB_HI_START = 0, MB_WORDS = 8 };
 
 struct CellsArgs {
     PairConsts pc;
-    int   N, Nalloc, G, nchunks;
-    int   nrows, nbx, ncells;
+    int   N, Nalloc, G, nchunks;    // global particle count; local slot capacity; grid; chunk capacity
+    int   nrows, nbx, ncells;       // global rows; bins per row; LOCAL cells = nlr * nbx
+    // slab decomposition over P GPUs (P == 1: one slab = the whole box, rows wrap around):
+    // this rank owns global rows [g0, g0 + nloc) = local rows [own_lo, own_lo + nloc) and, for P > 1,
+    // holds one halo row on each side (local rows 0 and nlr - 1)
+    int   P, me, g0, nloc, nlr, own_lo;    // me = this rank
+    float2*   peerR[2][LJMD_MAX_RANKS];      // every rank's position / velocity / index buffers,
+    float2*   peerV[2][LJMD_MAX_RANKS];      // cell counters, arrival words and mailbox (IPC-mapped)
+    int*      peerO[2][LJMD_MAX_RANKS];
+    int*      peer_cc[LJMD_MAX_RANKS];
+    unsigned* peer_flags[LJMD_MAX_RANKS];
+    int*      peer_mail[LJMD_MAX_RANKS];
+    int*      mail;                 // = peer_mail[rank]
+    int       nloc_of[LJMD_MAX_RANKS];       // owned rows of every rank
     float inv_hy, inv_wx, rlist2, half_skin2, dt;
     float2* R[2];
     float2* V[2];
@@ -100,6 +115,34 @@ struct CellsArgs {
 __device__ __forceinline__ int strip_coord(float x, float inv, int n) {
     const int c = (int)(x * inv);
     return max(0, min(c, n - 1));
+}
+
+// local row of a y coordinate (may be >= nlr: not held by this rank)
+__device__ __forceinline__ int local_row(const CellsArgs& a, float y) {
+    const int gr = strip_coord(y, a.inv_hy, a.nrows);
+    if (a.P == 1) return gr;
+    int lr = gr - a.g0 + 1;
+    lr += (lr < 0) ? a.nrows : 0;
+    lr -= (lr >= a.nrows) ? a.nrows : 0;
+    return lr;
+}
+__device__ __forceinline__ bool owned_row(const CellsArgs& a, int lr) {
+    return lr >= a.own_lo && lr < a.own_lo + a.nloc;
+}
+// stencil neighbour of an owned local row: wraps around for one slab, plain offset with halo rows
+__device__ __forceinline__ int nbr_row(const CellsArgs& a, int lr, int dr) {
+    int rr = lr + dr;
+    if (a.P == 1) {
+        rr += (rr < 0) ? a.nrows : 0;
+        rr -= (rr >= a.nrows) ? a.nrows : 0;
+    }
+    return rr;
+}
+// the particle needs the minimum image: first / last GLOBAL row, or within K bins of the x edges
+__device__ __forceinline__ bool edge_cell(const CellsArgs& a, int lr, int b) {
+    int gr = lr;
+    if (a.P > 1) { gr = a.g0 - 1 + lr; gr += (gr < 0) ? a.nrows : 0; gr -= (gr >= a.nrows) ? a.nrows : 0; }
+    return (gr == 0) | (gr == a.nrows - 1) | (b < CL_K) | (b > a.nbx - 1 - CL_K);
 }
 
 // block-wide exclusive scan of one int per thread; returns the exclusive prefix, *total = block sum
@@ -145,10 +188,49 @@ __device__ __forceinline__ double block_sum_array(const float* p, int n, double*
 }
 
 struct Ctx {
-    unsigned epoch;
+    unsigned epoch;     // grid-barrier epoch
+    unsigned xepoch;    // cross-GPU sync epoch
     int pr, pv;
+    int nheld;          // local slots in use (owned rows + halo rows)
+    int own_s, own_e;   // slot range of the owned rows
     long long* pt;      // shared-memory phase clocks (thread 0), or nullptr
 };
+
+// ---- cross-GPU synchronisation (slab decomposition) -----------------------------------------------
+// All ranks run the same steps in lockstep.  sync: every rank stamps an arrival word (epoch, plus one
+// payload bit) into every peer over NVLink after a system-scope fence, then every CTA waits until
+// all P local words carry the epoch.  Returns the OR of the payload bits.  Call after a grid barrier
+// (all of this rank's peer stores are then ordered before the stamp).
+__device__ __forceinline__ bool peer_sync(const CellsArgs& a, Ctx& ctx, bool payload) {
+    const unsigned xe = ++ctx.xepoch;
+    const int slot = (int)(xe & 1u) * a.P;          // words alternate by epoch: a peer that is already one
+                                                    // sync ahead does not overwrite a word still being read
+    if (blockIdx.x == 0 && threadIdx.x < a.P && (int)threadIdx.x != a.me) {
+        __threadfence_system();
+        volatile unsigned* f = a.peer_flags[threadIdx.x] + slot + a.me;
+        *f = (xe << 1) | (payload ? 1u : 0u);
+    }
+    __shared__ int s_any;
+    if (threadIdx.x == 0) {
+        const volatile unsigned* mine = a.peer_flags[a.me] + slot;
+        int any = payload ? 1 : 0;
+        long long t0 = clock64();
+        for (int q = 0; q < a.P; ++q) {
+            if (q == a.me) continue;
+            unsigned w;
+            while (((w = mine[q]) >> 1) != xe) {
+                if (clock64() - t0 > (1ll << 33)) { atomicOr(a.state + ST_ERR, CERR_PEER); w = 0u; break; }
+            }
+            any |= (int)(w & 1u);
+        }
+        __threadfence_system();
+        s_any = any;
+    }
+    __syncthreads();
+    const bool r = s_any != 0;
+    __syncthreads();
+    return r;
+}
 
 #define CL_PROF(k)                                                          \
     do {                                                                    \
@@ -168,21 +250,27 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
     const int tid = threadIdx.x, gtid = blockIdx.x * CL_THREADS + tid, gsz = a.G * CL_THREADS;
     const float2* __restrict__ Rc = a.R[ctx.pr];
     const int* __restrict__ orig_old = a.orig[ctx.pv];
-    const int N = a.N;
+    const int nheld = ctx.nheld;
+    const int lo_cell = a.own_lo * a.nbx, hi_cell = (a.own_lo + a.nloc) * a.nbx;   // owned local cells
     CL_PROF(0);
-    // B1: cell of every particle + histogram; the atomic's return value is the particle's (arbitrary)
-    //     arrival rank inside its cell, so the scatter needs no second atomic pass.  Four particles
-    //     per thread keep four atomics in flight.
+    // B1: cell of every held particle + histogram; the atomic's return value is the particle's
+    //     (arbitrary) arrival rank inside its cell, so the scatter needs no second atomic pass.  Four
+    //     particles per thread keep four atomics in flight.
+    //     Slabs: a rank re-bins the particles of its owned rows AND of its two halo rows (whose
+    //     positions and velocities the owners push every step) and keeps those that are now in an
+    //     owned row.  A particle moves less than one row between rebuilds, so whoever owns it next
+    //     already holds it: migration needs no message.
     //     (cell_count is all-zero on entry: cleared at create and again by B3 of every rebuild.)
-    for (int k0 = gtid; k0 < N; k0 += 4 * gsz) {
+    for (int k0 = gtid; k0 < nheld; k0 += 4 * gsz) {
         int c[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int k = k0 + u * gsz;
             c[u] = -1;
-            if (k < N) {
+            if (k < nheld) {
                 const float2 r = Rc[k];
-                c[u] = strip_coord(r.y, a.inv_hy, a.nrows) * a.nbx + strip_coord(r.x, a.inv_wx, a.nbx);
+                const int lr = local_row(a, r.y);
+                if (owned_row(a, lr)) c[u] = lr * a.nbx + strip_coord(r.x, a.inv_wx, a.nbx);
             }
         }
         int rk[4];
@@ -191,15 +279,28 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int k = k0 + u * gsz;
-            if (k < N) { a.key[k] = c[u]; a.rank[k] = rk[u]; }
+            if (k < nheld) { a.key[k] = c[u]; a.rank[k] = rk[u]; }
         }
     }
     CL_BARRIER();
+    if (a.P > 1) {
+        // H1: the bin populations of my first / last owned row are the populations of the lower
+        //     neighbour's upper halo row / the upper neighbour's lower halo row
+        const int dn = (a.me + a.P - 1) % a.P, up = (a.me + 1) % a.P;
+        int* cc_dn = a.peer_cc[dn] + (a.nloc_of[dn] + 1) * a.nbx;      // its local row nlr-1
+        int* cc_up = a.peer_cc[up];                                      // its local row 0
+        const int* mine_first = a.cell_count + lo_cell;
+        const int* mine_last  = a.cell_count + hi_cell - a.nbx;
+        for (int b = gtid; b < a.nbx; b += gsz) { cc_dn[b] = mine_first[b]; cc_up[b] = mine_last[b]; }
+        __threadfence_system();
+        CL_BARRIER();
+        (void)peer_sync(a, ctx, false);
+    }
     CL_PROF(2);
-    // B2: population of every row
-    for (int r = blockIdx.x; r < a.nrows; r += a.G) {
+    // B2: population of every local row
+    for (int r = blockIdx.x; r < a.nlr; r += a.G) {
         int s = 0;
-        for (int b = tid; b < a.nbx; b += CL_THREADS) s += a.cell_count[r * a.nbx + b];
+        for (int b = tid; b < a.nbx; b += CL_THREADS) s += __ldcg(&a.cell_count[r * a.nbx + b]);
         int tot;
         (void)block_exscan(s, sscan, &tot);
         if (tid == 0) a.row_tot[r] = tot;
@@ -208,7 +309,7 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
     CL_PROF(3);
     // B3: row offsets + in-row exclusive scan -> cell_start; the row's counters are cleared for the
     //     next rebuild.
-    for (int r = blockIdx.x; r < a.nrows; r += a.G) {
+    for (int r = blockIdx.x; r < a.nlr; r += a.G) {
         int s = 0;
         for (int q = tid; q < r; q += CL_THREADS) s += a.row_tot[q];
         int carry;
@@ -216,34 +317,45 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
         for (int bb = 0; bb < a.nbx; bb += CL_THREADS) {
             const int b = bb + tid;
             int v = 0;
-            if (b < a.nbx) { v = a.cell_count[r * a.nbx + b]; a.cell_count[r * a.nbx + b] = 0; }
+            if (b < a.nbx) { v = __ldcg(&a.cell_count[r * a.nbx + b]); a.cell_count[r * a.nbx + b] = 0; }
             int tot;
             const int ex = block_exscan(v, sscan, &tot);
             if (b < a.nbx) a.cell_start[r * a.nbx + b] = carry + ex;
             carry += tot;
         }
-        if (r == a.nrows - 1 && tid == 0) a.cell_start[a.ncells] = carry;
+        if (r == a.nlr - 1 && tid == 0) {
+            a.cell_start[a.ncells] = carry;
+            if (carry > a.Nalloc) atomicOr(a.state + ST_ERR, CERR_CAPACITY);
+        }
     }
     CL_BARRIER();
     CL_PROF(4);
+    const int own_s = a.cell_start[lo_cell], own_e = a.cell_start[hi_cell], nheld_new = a.cell_start[a.ncells];
+    if (a.P > 1 && gtid == 0) {
+        // H2: tell the upper neighbour where my upper halo row starts (it fills that row)
+        a.peer_mail[(a.me + 1) % a.P][MB_HI_START] = own_e;
+        __threadfence_system();
+    }
     // B4: scatter (source slot, original index, cell) into the cell's slot range, arrival order
-    for (int k0 = gtid; k0 < N; k0 += 4 * gsz) {
+    for (int k0 = gtid; k0 < nheld; k0 += 4 * gsz) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int k = k0 + u * gsz;
-            if (k < N) {
+            if (k < nheld) {
                 const int c = a.key[k];
-                const int d = a.cell_start[c] + a.rank[k];
-                a.tmpk[d] = k;
-                a.tmpo[d] = orig_old[k];
-                a.tmpc[d] = c;
+                if (c >= 0) {
+                    const int d = min(a.cell_start[c] + a.rank[k], a.Nalloc - 1);
+                    a.tmpk[d] = k;
+                    a.tmpo[d] = orig_old[k];
+                    a.tmpc[d] = c;
+                }
             }
         }
     }
     CL_BARRIER();
     CL_PROF(5);
-    // B5: each new slot picks the member of its cell whose ORIGINAL index has the slot's rank, so
-    //     the sorted order (cell, orig) is a pure function of the positions (bit-reproducible
+    // B5: each new owned slot picks the member of its cell whose ORIGINAL index has the slot's rank,
+    //     so the sorted order (cell, orig) is a pure function of the positions (bit-reproducible
     //     summation order downstream), then gathers that member's state (coalesced writes).
     //     (A bin holds ~1.6 particles at liquid density; a bin with more than CL_ORDER_MAX members
     //     keeps its arrival order: still correct, no longer run-to-run bit-reproducible.)
@@ -252,7 +364,7 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
         const float2* Vo = a.V[ctx.pv];
         float2* Vn = a.V[ctx.pv ^ 1];
         int* on = a.orig[ctx.pv ^ 1];
-        for (int d = gtid; d < N; d += gsz) {
+        for (int d = own_s + gtid; d < own_e; d += gsz) {
             const int c = a.tmpc[d];
             const int b = a.cell_start[c], n = a.cell_start[c + 1] - b, p = d - b;
             int msel = p;
@@ -274,8 +386,44 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
     }
     ctx.pr ^= 1;
     ctx.pv ^= 1;
+    ctx.nheld = nheld_new;
+    ctx.own_s = own_s;
+    ctx.own_e = own_e;
     if (blockIdx.x == 0 && tid == 0) a.state[ST_REBUILDS] += 1;
     CL_BARRIER();
+    if (a.P > 1) {
+        // H3: my first / last owned row, freshly sorted, becomes the neighbours' halo row: positions,
+        //     velocities and original indices (a halo particle may become theirs at the next
+        //     rebuild).  One sync before, so that every rank has
+        //     published where its upper halo row starts and is done reading its old buffers.
+        (void)peer_sync(a, ctx, false);
+        const int dn = (a.me + a.P - 1) % a.P, up = (a.me + 1) % a.P;
+        const int first_s = own_s, first_e = a.cell_start[lo_cell + a.nbx];
+        const int last_s = a.cell_start[hi_cell - a.nbx], last_e = own_e;
+        const int peer_hi_start = __ldcg(&a.mail[MB_HI_START]);   // mailed by the lower neighbour (H2)
+        const float2* Rn = a.R[ctx.pr];
+        const float2* Vn = a.V[ctx.pv];
+        const int* on = a.orig[ctx.pv];
+        // my first owned row -> lower neighbour's upper halo row (starts at the slot it mailed me)
+        {
+            float2* pR = a.peerR[ctx.pr][dn]; float2* pV = a.peerV[ctx.pv][dn]; int* pO = a.peerO[ctx.pv][dn];
+            for (int i = first_s + gtid; i < first_e; i += gsz) {
+                const int j = peer_hi_start + (i - first_s);
+                pR[j] = Rn[i]; pV[j] = Vn[i]; pO[j] = on[i];
+            }
+        }
+        // my last owned row -> upper neighbour's lower halo row (starts at its slot 0)
+        {
+            float2* pR = a.peerR[ctx.pr][up]; float2* pV = a.peerV[ctx.pv][up]; int* pO = a.peerO[ctx.pv][up];
+            for (int i = last_s + gtid; i < last_e; i += gsz) {
+                const int j = i - last_s;
+                pR[j] = Rn[i]; pV[j] = Vn[i]; pO[j] = on[i];
+            }
+        }
+        __threadfence_system();
+        CL_BARRIER();
+        (void)peer_sync(a, ctx, false);
+    }
     CL_PROF(6);
     // B6: bitmask Verlet list.  For each stencil row the candidate bins [b-K, b+K] (periodic: up to
     //     two pieces) form contiguous slot ranges; every 32 slots of a range with at least one
@@ -289,18 +437,18 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
         const int* __restrict__ cs = a.cell_start;
         const PairConsts pc = a.pc;
         const int lane = tid & 31;
-        for (int i0 = (gtid & ~31); i0 < N; i0 += gsz) {
+        for (int i0 = (ctx.own_s & ~31) + (gtid & ~31); i0 < ctx.own_e; i0 += gsz) {
             const int i = i0 + lane;
-            const bool live = i < N;
+            const bool live = (i >= ctx.own_s) & (i < ctx.own_e);
             float2 ri = make_float2(0.0f, 0.0f);
             int c = 0;
             if (live) { ri = R[i]; c = a.tmpc[i]; }
-            const int r = c / a.nbx, b = c - r * a.nbx;
-            const bool edge = (r == 0) | (r == a.nrows - 1) | (b < CL_K) | (b > a.nbx - 1 - CL_K);
+            const int r = c / a.nbx, b = c - r * a.nbx;           // local row, bin
+            const bool edge = edge_cell(a, r, b);
             // warp plan
-            const int nl = min(32, N - i0);
-            const int r_first = __shfl_sync(0xffffffffu, r, 0), r_last = __shfl_sync(0xffffffffu, r, nl - 1);
-            const int b_first = __shfl_sync(0xffffffffu, b, 0), b_last = __shfl_sync(0xffffffffu, b, nl - 1);
+            const int l_first = max(ctx.own_s - i0, 0), l_last = min(31, ctx.own_e - 1 - i0);
+            const int r_first = __shfl_sync(0xffffffffu, r, l_first), r_last = __shfl_sync(0xffffffffu, r, l_last);
+            const int b_first = __shfl_sync(0xffffffffu, b, l_first), b_last = __shfl_sync(0xffffffffu, b, l_last);
             bool staged = (a.mode == 0) && (r_first == r_last) && !__any_sync(0xffffffffu, live && edge);
             int ws[3] = {0, 0, 0}, wn[3] = {0, 0, 0};
             if (staged) {
@@ -374,9 +522,7 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
             } else if (live) {
                 const int lo = b - CL_K, hi = b + CL_K;
                 for (int k = 0; k < 3; ++k) {
-                    int rr = r + k - 1;
-                    rr += (rr < 0) ? a.nrows : 0;
-                    rr -= (rr >= a.nrows) ? a.nrows : 0;
+                    const int rr = nbr_row(a, r, k - 1);
                     const int* __restrict__ csr = cs + rr * a.nbx;
                     for (int piece = 0; piece < 3; ++piece) {
                         int bl, bh;
@@ -544,6 +690,10 @@ cells_persistent_kernel(const CellsArgs a) {
     if (ctx.pt && tid == 0) { for (int k = 0; k < 11; ++k) s_pt[k] = 0; s_pt[11] = clock64(); }
     ctx.pr = a.state[ST_PR];
     ctx.pv = a.state[ST_PV];
+    ctx.nheld = a.state[ST_NHELD];
+    ctx.own_s = a.state[ST_OWN_S];
+    ctx.own_e = a.state[ST_OWN_E];
+    ctx.xepoch = (unsigned)a.state[ST_XEPOCH];
     // per warp: staged neighbour windows (+ sentinel slots) and the byte rows of the list build
     float2* my_win = reinterpret_cast<float2*>(cells_smem + (size_t)(tid >> 5) * CL_WARP_SMEM);
     unsigned char* my_bytes = cells_smem + (size_t)(tid >> 5) * CL_WARP_SMEM + CL_WSLOTS * 8;
@@ -552,11 +702,32 @@ cells_persistent_kernel(const CellsArgs a) {
     __syncthreads();
 
     if (a.s_begin < 0) {
-        // load the caller's state (original order) and sort it
-        for (int i = gtid; i < a.N; i += gsz) {
-            a.R[ctx.pr][i] = a.R_in[i];
-            a.V[ctx.pv][i] = a.V_in ? a.V_in[i] : make_float2(0.0f, 0.0f);
-            a.orig[ctx.pv][i] = i;
+        // load the caller's state (original order) and sort it.  Slabs: every rank reads the whole
+        // (replicated) input and keeps the particles of its owned rows, in arrival order (the sort
+        // orders them); the halo rows are filled by the neighbours during the rebuild.
+        if (a.P == 1) {
+            for (int i = gtid; i < a.N; i += gsz) {
+                a.R[ctx.pr][i] = a.R_in[i];
+                a.V[ctx.pv][i] = a.V_in ? a.V_in[i] : make_float2(0.0f, 0.0f);
+                a.orig[ctx.pv][i] = i;
+            }
+            ctx.nheld = a.N;
+        } else {
+            for (int i = gtid; i < a.N; i += gsz) {
+                const float2 r = a.R_in[i];
+                if (owned_row(a, local_row(a, r.y))) {
+                    const int k = atomicAdd(a.state + ST_LOADCNT, 1);
+                    if (k < a.Nalloc) {
+                        a.R[ctx.pr][k] = r;
+                        a.V[ctx.pv][k] = a.V_in ? a.V_in[i] : make_float2(0.0f, 0.0f);
+                        a.orig[ctx.pv][k] = i;
+                    } else {
+                        atomicOr(a.state + ST_ERR, CERR_CAPACITY);
+                    }
+                }
+            }
+            CL_BARRIER();
+            ctx.nheld = min(__ldcg(a.state + ST_LOADCNT), a.Nalloc);
         }
         CL_BARRIER();
         cells_rebuild(a, ctx, sscan, my_win, my_bytes, (a.mode == 1) ? a.count_r2 : a.rlist2);
@@ -583,6 +754,7 @@ cells_persistent_kernel(const CellsArgs a) {
         if (s > a.s_begin || a.s_begin >= 0) {
             if (__ldcg(a.state + ST_FLAG) == (int)(s + 1)) cells_rebuild(a, ctx, sscan, my_win, my_bytes, a.rlist2);
         }
+        // (slabs: ST_FLAG holds the decision of ALL ranks, see the end of the step)
         const float2* __restrict__ R = a.R[ctx.pr];
         float2*       Rnext = a.R[ctx.pr ^ 1];
         float2*       V     = a.V[ctx.pv];
@@ -592,23 +764,34 @@ cells_persistent_kernel(const CellsArgs a) {
         // chunks ahead by thread 0): rows differ in density and edge warps are slower, a static
         // split leaves CTAs idle at the barrier.  No result depends on which CTA ran a chunk.
         if (gtid == 0) __stcg(&a.sched[par ^ 1], 0);     // the other parity's counter: idle this step
+        // chunks are aligned to multiples of CL_THREADS slots (the warp plans are per 32 aligned
+        // slots); the owned slot range may start and end inside a chunk
+        const int ch_lo = ctx.own_s / CL_THREADS, ch_hi = (ctx.own_e + CL_THREADS - 1) / CL_THREADS;
+        // halo pushes (slabs): slots of my first / last owned row and where they live in the neighbours
+        const int dn = (a.me + a.P - 1) % a.P, up = (a.me + 1) % a.P;
+        int first_e = 0, last_s = 0, peer_hi_start = 0;
+        if (a.P > 1) {
+            first_e = a.cell_start[(a.own_lo + 1) * a.nbx];
+            last_s = a.cell_start[(a.own_lo + a.nloc - 1) * a.nbx];
+            peer_hi_start = __ldcg(&a.mail[MB_HI_START]);
+        }
         int c_cur = 0, c_nxt = 0;
-        if (tid == 0) { c_cur = atomicAdd(&a.sched[par], 1); c_nxt = atomicAdd(&a.sched[par], 1); }
+        if (tid == 0) { c_cur = ch_lo + atomicAdd(&a.sched[par], 1); c_nxt = ch_lo + atomicAdd(&a.sched[par], 1); }
         int moved = 0;
         for (int it = 0;; ++it) {
             if (tid == 0) { s_ch[it & 1][0] = c_cur; s_ch[it & 1][1] = c_nxt; }
             __syncthreads();
             const int ch = s_ch[it & 1][0], chn = s_ch[it & 1][1];
-            if (ch >= a.nchunks) break;
-            if (tid == 0) { c_cur = c_nxt; c_nxt = atomicAdd(&a.sched[par], 1); }
+            if (ch >= ch_hi) break;
+            if (tid == 0) { c_cur = c_nxt; c_nxt = ch_lo + atomicAdd(&a.sched[par], 1); }
             const int  i    = ch * CL_THREADS + tid;
-            const bool live = i < a.N;
+            const bool live = (i >= ctx.own_s) & (i < ctx.own_e);
             // The pass streams ~70 bytes per particle and a warp has one particle per lane in flight:
             // without help the SM holds too few bytes in flight to cover the HBM latency.  Request the
             // NEXT chunk's operands now (L2 -> L1 prefetch); they arrive while this chunk is evaluated.
             {
                 const int inext = chn * CL_THREADS + tid;
-                if (inext < a.N) {
+                if (inext < ctx.own_e) {
                     prefetch_l1(R + inext);
                     prefetch_l1(a.meta + inext);
 #pragma unroll
@@ -629,7 +812,7 @@ cells_persistent_kernel(const CellsArgs a) {
             const int ii = live ? i : 0;
             // the warp's three neighbour windows -> shared memory (coalesced), then LDS gathers
             const int wid = i >> 5;
-            const int4 p0 = (wid * 32 < a.N) ? a.wplan[2 * wid] : make_int4(0, 0, 0, 0);
+            const int4 p0 = (wid * 32 < ctx.own_e && wid * 32 + 32 > ctx.own_s) ? a.wplan[2 * wid] : make_int4(0, 0, 0, 0);
             const bool staged = p0.w != 0;
             float2* win = my_win;
             if (staged) {
@@ -670,6 +853,18 @@ cells_persistent_kernel(const CellsArgs a) {
                     const float2 rn = make_float2(drift(ri.x, v.x, a.dt, a.pc.box),               // MD:71-72
                                                   drift(ri.y, v.y, a.dt, a.pc.box));
                     Rnext[i] = rn;
+                    if (a.P > 1) {
+                        // halo exchange: the new position and velocity of a boundary-row particle go
+                        // straight into the neighbour's halo slot (NVLink peer store)
+                        if (i < first_e) {
+                            const int j = peer_hi_start + (i - ctx.own_s);
+                            a.peerR[ctx.pr ^ 1][dn][j] = rn; a.peerV[ctx.pv][dn][j] = v;
+                        }
+                        if (i >= last_s) {
+                            const int j = i - last_s;
+                            a.peerR[ctx.pr ^ 1][up][j] = rn; a.peerV[ctx.pv][up][j] = v;
+                        }
+                    }
                     const float ddx = min_image(__fsub_rn(rn.x, rb.x), a.pc.box, a.pc.timg);
                     const float ddy = min_image(__fsub_rn(rn.y, rb.y), a.pc.box, a.pc.timg);
                     moved |= (ddx * ddx + ddy * ddy > a.half_skin2);
@@ -687,11 +882,11 @@ cells_persistent_kernel(const CellsArgs a) {
         }
         if (thermo) {
             CL_BARRIER();
-            const double ke2 = block_sum_array(a.ke_part + par * a.nchunks, a.nchunks, sdbl);
+            const double ke2 = block_sum_array(a.ke_part + par * a.nchunks + ch_lo, ch_hi - ch_lo, sdbl);
             if (tid == 0) s_lambda = sqrtf(rc.thermo_kT / ((float)(0.5 * ke2) / (float)a.N));
             __syncthreads();
             const float lam = s_lambda;
-            for (int i = gtid; i < a.N; i += gsz) {
+            for (int i = ctx.own_s + gtid; i < ctx.own_e; i += gsz) {
                 const float2 ri = R[i];
                 const float2 F = a.Fs[i];
                 float2 v = V[i];
@@ -716,16 +911,26 @@ cells_persistent_kernel(const CellsArgs a) {
         }
         // a particle left the skin/2 ball: ask for a rebuild before the next force evaluation.
         // The flag carries the step stamp, so it never needs clearing (no reset race).
-        if (__syncthreads_or(moved) && tid == 0) __stcg(a.state + ST_FLAG, (int)(s + 2));
+        if (__syncthreads_or(moved) && tid == 0) __stcg(a.state + (a.P > 1 ? ST_LMOVED : ST_FLAG), (int)(s + 2));
+        if (a.P > 1) __threadfence_system();                 // halo pushes visible before the arrival word
         if (!final) ctx.pr ^= 1;
         CL_PROF(0);
         CL_BARRIER();
+        if (a.P > 1 && !final) {
+            // one NVLink round trip per step: every rank's halo pushes have landed once all arrival
+            // words carry this epoch; the words also carry "one of my particles left its skin/2 ball",
+            // so that all ranks rebuild at the same step
+            const bool mine = (__ldcg(a.state + ST_LMOVED) == (int)(s + 2));
+            const bool any = peer_sync(a, ctx, mine);
+            if (any && gtid == 0) __stcg(a.state + ST_FLAG, (int)(s + 2));
+            if (any) CL_BARRIER();                           // (rare) the flag is read at the next step
+        }
         CL_PROF(1);
 
         if (blockIdx.x == 0 && want_pe) {
-            const double pe2 = block_sum_array(a.pe_part + par * a.nchunks, a.nchunks, sdbl);
+            const double pe2 = block_sum_array(a.pe_part + par * a.nchunks + ch_lo, ch_hi - ch_lo, sdbl);
             double ke2 = 0.0;
-            if (want_e) ke2 = block_sum_array(a.ke_part + par * a.nchunks, a.nchunks, sdbl);
+            if (want_e) ke2 = block_sum_array(a.ke_part + par * a.nchunks + ch_lo, ch_hi - ch_lo, sdbl);
             if (tid == 0) {
                 if (want_e) {
                     float* o = rc.ke_pe + 2 * (s / rc.energy_every);
@@ -737,7 +942,11 @@ cells_persistent_kernel(const CellsArgs a) {
             }
         }
     }
-    if (gtid == 0) { a.state[ST_PR] = ctx.pr; a.state[ST_PV] = ctx.pv; }
+    if (gtid == 0) {
+        a.state[ST_PR] = ctx.pr; a.state[ST_PV] = ctx.pv;
+        a.state[ST_NHELD] = ctx.nheld; a.state[ST_OWN_S] = ctx.own_s; a.state[ST_OWN_E] = ctx.own_e;
+        a.state[ST_XEPOCH] = (int)ctx.xepoch;
+    }
     if (ctx.pt && tid == 0)
         for (int k = 0; k < 11; ++k) a.prof[blockIdx.x * 12 + k] = s_pt[k];
 }
@@ -758,11 +967,17 @@ __global__ void cell_assign_kernel(const float2* __restrict__ R, int N, int nrow
 // ----------------------------------------------------------------------------------------------------
 struct Cells {
     int G = 0, nrows = 0, nbx = 0, ncells = 0, Nalloc = 0, nchunks = 0;
+    int P = 1, g0 = 0, nloc = 0, nlr = 0, own_lo = 0, ncells_max = 0;
+    int nloc_of[LJMD_MAX_RANKS] = {};
     float inv_hy = 0, inv_wx = 0, hy = 0, wx = 0, rlist = 0;
-    float2 *R[2] = {nullptr, nullptr}, *V[2] = {nullptr, nullptr}, *Rb = nullptr, *Fs = nullptr;
-    int *orig[2] = {nullptr, nullptr};
+    // one allocation (IPC-shared with the peers when P > 1): R[2], V[2], orig[2], cell_count, arrival
+    // words, mailbox -- at the same offsets on every rank
+    void* shared = nullptr;
+    size_t off_R[2] = {}, off_V[2] = {}, off_O[2] = {}, off_cc = 0, off_flags = 0, off_mail = 0;
+    char* peer_base[LJMD_MAX_RANKS] = {};
+    float2 *Rb = nullptr, *Fs = nullptr;
     int *key = nullptr, *rank = nullptr, *tmpk = nullptr, *tmpo = nullptr, *tmpc = nullptr,
-        *cell_count = nullptr, *cell_start = nullptr, *row_tot = nullptr;
+        *cell_start = nullptr, *row_tot = nullptr;
     unsigned* meta = nullptr;
     uint2* ent = nullptr;
     unsigned* nb4 = nullptr;
@@ -778,6 +993,8 @@ int cells_create(ljmd_handle* h) {
     Cells* cl = new Cells();
     h->cells = cl;
     const long long N = h->p.N;
+    const int P = h->nranks;
+    cl->P = P;
     if (N > (1ll << 30)) { set_error("N too large for 32-bit particle indices"); return LJMD_E_INVALID; }
     const float rc = h->p.rc, skin = h->p.skin;
     cl->rlist = rc + skin;
@@ -792,13 +1009,36 @@ int cells_create(ljmd_handle* h) {
         return LJMD_E_INVALID;
     }
     if ((long long)cl->nrows * cl->nbx > (1ll << 30)) { set_error("cell index too large"); return LJMD_E_INVALID; }
-    cl->ncells = cl->nrows * cl->nbx;
     cl->hy = h->p.box / (float)cl->nrows;
     cl->wx = h->p.box / (float)cl->nbx;
     cl->inv_hy = (float)cl->nrows / h->p.box;
     cl->inv_wx = (float)cl->nbx / h->p.box;
-    cl->Nalloc = (int)(((N + 63) / 64) * 64);
-    cl->nchunks = (int)((N + CL_THREADS - 1) / CL_THREADS);
+    // slab decomposition: contiguous blocks of rows, as even as possible; one halo row per side
+    if (P > 1 && cl->nrows < 2 * P) {
+        set_error("cell list: %d rows cannot be split over %d GPUs (need 2 rows per GPU)", cl->nrows, P);
+        return LJMD_E_INVALID;
+    }
+    int g = 0, maxloc = 0;
+    for (int q = 0; q < P; ++q) {
+        cl->nloc_of[q] = cl->nrows / P + (q < cl->nrows % P ? 1 : 0);
+        if (q == h->rank) cl->g0 = g;
+        g += cl->nloc_of[q];
+        maxloc = std::max(maxloc, cl->nloc_of[q]);
+    }
+    cl->nloc = cl->nloc_of[h->rank];
+    cl->own_lo = (P > 1) ? 1 : 0;
+    cl->nlr = cl->nloc + 2 * cl->own_lo;
+    cl->ncells = cl->nlr * cl->nbx;
+    cl->ncells_max = (maxloc + 2 * cl->own_lo) * cl->nbx;
+    if (P == 1) {
+        cl->Nalloc = (int)(((N + 63) / 64) * 64);
+    } else {
+        // owned rows + two halo rows, with room for density fluctuations between slabs
+        const double per = (double)N / P;
+        const double row = (double)N / cl->nrows;
+        cl->Nalloc = (int)((((long long)(1.35 * per + 6.0 * row) + 4096 + 63) / 64) * 64);
+    }
+    cl->nchunks = cl->Nalloc / CL_THREADS + 2;
 
     const size_t smem = (size_t)CL_WARPS * CL_WARP_SMEM;
     LJ_CUDA(cudaFuncSetAttribute(cells_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -806,15 +1046,30 @@ int cells_create(ljmd_handle* h) {
     LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cells_persistent_kernel, CL_THREADS, smem));
     if (per_sm < 1) { set_error("cell-list kernel does not fit on an SM"); return LJMD_E_STATE; }
     if (const char* e = getenv("LJMD_CELLS_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));
-    long long g = (long long)per_sm * h->num_sms;
-    g = std::min<long long>(g, std::max<long long>(1, cl->nchunks));
-    cl->G = (int)g;
+    long long gg = (long long)per_sm * h->num_sms;
+    gg = std::min<long long>(gg, std::max<long long>(1, (N / P + CL_THREADS - 1) / CL_THREADS));
+    cl->G = (int)gg;
 
     const size_t na = (size_t)cl->Nalloc;
-    for (int k = 0; k < 2; ++k) {
-        LJ_CUDA(cudaMalloc(&cl->R[k], sizeof(float2) * na));
-        LJ_CUDA(cudaMalloc(&cl->V[k], sizeof(float2) * na));
-        LJ_CUDA(cudaMalloc(&cl->orig[k], sizeof(int) * na));
+    {   // the shared allocation
+        auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+        size_t off = 0;
+        for (int k = 0; k < 2; ++k) { cl->off_R[k] = off; off += up(sizeof(float2) * na); }
+        for (int k = 0; k < 2; ++k) { cl->off_V[k] = off; off += up(sizeof(float2) * na); }
+        for (int k = 0; k < 2; ++k) { cl->off_O[k] = off; off += up(sizeof(int) * na); }
+        cl->off_cc = off;    off += up(sizeof(int) * (size_t)cl->ncells_max);
+        cl->off_flags = off; off += up(sizeof(unsigned) * 2 * LJMD_MAX_RANKS);
+        cl->off_mail = off;  off += up(sizeof(int) * MB_WORDS);
+        const size_t bytes = std::max<size_t>((off + (2u << 20) - 1) / (2u << 20) * (2u << 20), 4u << 20);
+        LJ_CUDA(cudaMalloc(&cl->shared, bytes));
+        LJ_CUDA(cudaMemset(cl->shared, 0, bytes));
+        cl->peer_base[h->rank] = reinterpret_cast<char*>(cl->shared);
+        if (P > 1) {
+            void* peers[LJMD_MAX_RANKS];
+            int r = dist_share(h, cl->shared, peers);
+            if (r) return r;
+            for (int q = 0; q < P; ++q) cl->peer_base[q] = reinterpret_cast<char*>(peers[q]);
+        }
     }
     LJ_CUDA(cudaMalloc(&cl->Rb, sizeof(float2) * na));
     LJ_CUDA(cudaMalloc(&cl->Fs, sizeof(float2) * na));
@@ -827,10 +1082,8 @@ int cells_create(ljmd_handle* h) {
     LJ_CUDA(cudaMalloc(&cl->ent, sizeof(uint2) * na * CL_E));
     LJ_CUDA(cudaMalloc(&cl->wplan, sizeof(int4) * 2 * (na / 32 + 1)));
     LJ_CUDA(cudaMalloc(&cl->nb4, sizeof(unsigned) * na * CL_NW));
-    LJ_CUDA(cudaMalloc(&cl->cell_count, sizeof(int) * (size_t)cl->ncells));
-    LJ_CUDA(cudaMemset(cl->cell_count, 0, sizeof(int) * (size_t)cl->ncells));
     LJ_CUDA(cudaMalloc(&cl->cell_start, sizeof(int) * ((size_t)cl->ncells + 1)));
-    LJ_CUDA(cudaMalloc(&cl->row_tot, sizeof(int) * (size_t)cl->nrows));
+    LJ_CUDA(cudaMalloc(&cl->row_tot, sizeof(int) * (size_t)cl->nlr));
     LJ_CUDA(cudaMalloc(&cl->pe_part, sizeof(float) * 2 * cl->nchunks));
     LJ_CUDA(cudaMalloc(&cl->ke_part, sizeof(float) * 2 * cl->nchunks));
     LJ_CUDA(cudaMalloc(&cl->state, sizeof(int) * ST_WORDS));
@@ -844,10 +1097,11 @@ int cells_create(ljmd_handle* h) {
 void cells_destroy(ljmd_handle* h) {
     Cells* cl = h->cells;
     if (!cl) return;
-    for (int k = 0; k < 2; ++k) { cudaFree(cl->R[k]); cudaFree(cl->V[k]); cudaFree(cl->orig[k]); }
+    cudaFree(cl->shared);
     cudaFree(cl->Rb); cudaFree(cl->Fs); cudaFree(cl->key); cudaFree(cl->rank);
-    cudaFree(cl->tmpk); cudaFree(cl->tmpo); cudaFree(cl->tmpc); cudaFree(cl->meta); cudaFree(cl->ent); cudaFree(cl->wplan); cudaFree(cl->nb4);
-    cudaFree(cl->cell_count); cudaFree(cl->cell_start); cudaFree(cl->row_tot);
+    cudaFree(cl->tmpk); cudaFree(cl->tmpo); cudaFree(cl->tmpc); cudaFree(cl->meta);
+    cudaFree(cl->ent); cudaFree(cl->wplan); cudaFree(cl->nb4);
+    cudaFree(cl->cell_start); cudaFree(cl->row_tot);
     cudaFree(cl->pe_part); cudaFree(cl->ke_part);
     cudaFree(cl->state); cudaFree(cl->bar); cudaFree(cl->prof); cudaFree(cl->sched);
     delete cl;
@@ -859,14 +1113,29 @@ static void fill_args(ljmd_handle* h, CellsArgs& a) {
     a.pc = h->pc;
     a.N = (int)h->p.N; a.Nalloc = cl->Nalloc; a.G = cl->G; a.nchunks = cl->nchunks;
     a.nrows = cl->nrows; a.nbx = cl->nbx; a.ncells = cl->ncells;
+    a.P = cl->P; a.me = h->rank; a.g0 = cl->g0; a.nloc = cl->nloc; a.nlr = cl->nlr; a.own_lo = cl->own_lo;
+    for (int q = 0; q < LJMD_MAX_RANKS; ++q) a.nloc_of[q] = cl->nloc_of[q];
     a.inv_hy = cl->inv_hy; a.inv_wx = cl->inv_wx;
     a.rlist2 = cl->rlist * cl->rlist;
     a.half_skin2 = (0.5f * h->p.skin) * (0.5f * h->p.skin);
     a.dt = h->p.dt;
-    for (int k = 0; k < 2; ++k) { a.R[k] = cl->R[k]; a.V[k] = cl->V[k]; a.orig[k] = cl->orig[k]; }
+    for (int q = 0; q < cl->P; ++q) {
+        char* base = cl->peer_base[q];
+        for (int k = 0; k < 2; ++k) {
+            a.peerR[k][q] = reinterpret_cast<float2*>(base + cl->off_R[k]);
+            a.peerV[k][q] = reinterpret_cast<float2*>(base + cl->off_V[k]);
+            a.peerO[k][q] = reinterpret_cast<int*>(base + cl->off_O[k]);
+        }
+        a.peer_cc[q] = reinterpret_cast<int*>(base + cl->off_cc);
+        a.peer_flags[q] = reinterpret_cast<unsigned*>(base + cl->off_flags);
+        a.peer_mail[q] = reinterpret_cast<int*>(base + cl->off_mail);
+    }
+    for (int k = 0; k < 2; ++k) { a.R[k] = a.peerR[k][h->rank]; a.V[k] = a.peerV[k][h->rank]; a.orig[k] = a.peerO[k][h->rank]; }
+    a.cell_count = a.peer_cc[h->rank];
+    a.mail = a.peer_mail[h->rank];
     a.Rb = cl->Rb; a.Fs = cl->Fs;
     a.key = cl->key; a.rank = cl->rank; a.tmpk = cl->tmpk; a.tmpo = cl->tmpo; a.tmpc = cl->tmpc;
-    a.cell_count = cl->cell_count; a.cell_start = cl->cell_start; a.row_tot = cl->row_tot;
+    a.cell_start = cl->cell_start; a.row_tot = cl->row_tot;
     a.meta = cl->meta; a.ent = cl->ent; a.wplan = cl->wplan; a.nb4 = cl->nb4;
     a.pe_part = cl->pe_part; a.ke_part = cl->ke_part;
     a.state = cl->state; a.bar = cl->bar; a.prof = cl->prof; a.sched = cl->sched;
@@ -887,12 +1156,28 @@ int cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_
               float2* F_out, float* pe_out, const RunCtl& rc) {
     Cells* cl = h->cells;
     const long long N = h->p.N;
+    const int P = cl->P;
     cudaStream_t st = h->stream;
+    if (P > 1) {
+        if (rc.thermo_every > 0 && rc.thermo_kT > 0.0f) {
+            set_error("the thermostat is not available on the multi-GPU cell-list path");
+            return LJMD_E_UNSUPPORTED;
+        }
+        if ((R_out && R_out == R_in) || (V_out && V_out == V_in)) {
+            set_error("multi-GPU cell-list path: outputs must not alias the inputs");
+            return LJMD_E_UNSUPPORTED;
+        }
+        // every rank writes only the particles it owns; the replicated result is the sum
+        if (R_out) LJ_CUDA(cudaMemsetAsync(R_out, 0, sizeof(float2) * N, st));
+        if (V_out) LJ_CUDA(cudaMemsetAsync(V_out, 0, sizeof(float2) * N, st));
+        if (F_out) LJ_CUDA(cudaMemsetAsync(F_out, 0, sizeof(float2) * N, st));
+    }
     if (rc.nsteps > 0 && rc.traj && rc.S > 0)
         LJ_CUDA(cudaMemsetAsync(rc.traj, 0, sizeof(float2) * N * rc.S, st));      // MD:89
-    // fresh call: parities 0, rebuild counter 0, flag 0 (the error word is sticky)
+    // fresh call: parities 0, rebuild counter 0, flags 0 (the error word and the cross-GPU epoch persist)
     LJ_CUDA(cudaMemsetAsync(cl->state, 0, sizeof(int) * 3, st));
-    LJ_CUDA(cudaMemsetAsync(cl->state + ST_FLAG, 0, sizeof(int), st));
+    LJ_CUDA(cudaMemsetAsync(cl->state + ST_FLAG, 0, sizeof(int) * (ST_XEPOCH - ST_FLAG), st));
+    LJ_CUDA(cudaMemsetAsync(cl->state + ST_LMOVED, 0, sizeof(int), st));
     CellsArgs a{};
     fill_args(h, a);
     a.R_in = R_in; a.V_in = V_in;
@@ -911,6 +1196,19 @@ int cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_
         if (r) return r;
         s = a.s_end;
         if (rc.nsteps == 0) break;
+    }
+    if (P > 1) {
+        // replicated out (NCCL over NVLink, once per call): owner-written entries + zeros elsewhere
+        int r = 0;
+        if (R_out && (r = dist_allreduce_f32(h, reinterpret_cast<float*>(R_out), (size_t)2 * N))) return r;
+        if (V_out && (r = dist_allreduce_f32(h, reinterpret_cast<float*>(V_out), (size_t)2 * N))) return r;
+        if (F_out && (r = dist_allreduce_f32(h, reinterpret_cast<float*>(F_out), (size_t)2 * N))) return r;
+        if (rc.traj && rc.S > 0 && (r = dist_allreduce_f32(h, reinterpret_cast<float*>(rc.traj), (size_t)2 * N * rc.S))) return r;
+        if (pe_out && (r = dist_allreduce_f32(h, pe_out, 1))) return r;
+        if (rc.ke_pe && rc.energy_every > 0) {       // "energies use one NCCL all-reduce"
+            const long long ne = (rc.nsteps + rc.energy_every - 1) / rc.energy_every;
+            if ((r = dist_allreduce_f32(h, rc.ke_pe, (size_t)(2 * ne)))) return r;
+        }
     }
     if (h->timed) LJ_CUDA(cudaEventRecord(h->ev1, st));
     if (cl->prof) {   // debug: mean clocks per phase of the LAST launch, summed over its steps
@@ -941,7 +1239,7 @@ int cells_geometry(ljmd_handle* h, int* nrows, int* nbx, int* kbins, float* inv_
 int cells_assign(ljmd_handle* h, const float2* R, int* cell_id, int* cell_count) {
     Cells* cl = h->cells;
     const int N = (int)h->p.N;
-    if (cell_count) LJ_CUDA(cudaMemsetAsync(cell_count, 0, sizeof(int) * (size_t)cl->ncells, h->stream));
+    if (cell_count) LJ_CUDA(cudaMemsetAsync(cell_count, 0, sizeof(int) * (size_t)cl->nrows * cl->nbx, h->stream));
     cell_assign_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(R, N, cl->nrows, cl->nbx, cl->inv_hy,
                                                                cl->inv_wx, cell_id, cell_count);
     LJ_CUDA(cudaGetLastError());
@@ -955,8 +1253,9 @@ int cells_neighbor_count(ljmd_handle* h, const float2* R, float radius, int* nbr
         set_error("neighbor_count radius %.4f must be in (0, rc + skin = %.4f]", radius, cl->rlist);
         return LJMD_E_INVALID;
     }
+    if (cl->P > 1) { set_error("neighbor_count is single-GPU only"); return LJMD_E_UNSUPPORTED; }
     LJ_CUDA(cudaMemsetAsync(cl->state, 0, sizeof(int) * 3, h->stream));
-    LJ_CUDA(cudaMemsetAsync(cl->state + ST_FLAG, 0, sizeof(int), h->stream));
+    LJ_CUDA(cudaMemsetAsync(cl->state + ST_FLAG, 0, sizeof(int) * (ST_XEPOCH - ST_FLAG), h->stream));
     CellsArgs a{};
     fill_args(h, a);
     a.R_in = R; a.V_in = nullptr;
@@ -984,6 +1283,8 @@ int cells_check_error(ljmd_handle* h) {
         set_error("cell-list: a particle needs more than %d list entries (too dense for rc+skin)", CL_E);
         return LJMD_E_STATE;
     }
+    if (e & CERR_CAPACITY) { set_error("cell-list: a slab holds more particles than its buffers (density too uneven)"); return LJMD_E_STATE; }
+    if (e & CERR_PEER) { set_error("cell-list: a peer GPU did not arrive at a cross-GPU synchronisation"); return LJMD_E_STATE; }
     if (e) { set_error("cell-list persistent kernel: grid barrier timed out (flag %d)", e); return LJMD_E_STATE; }
     return 0;
 }
