@@ -8,10 +8,12 @@ pass of the hot path over one batch: ``md_steps_per_step`` velocity-Verlet steps
 system issued as ONE device dispatch (like equilibrate_fn, MD:77-83).
 
 Workloads (BASELINE.json configs):
-  ap4096   all-pairs N=4,096  rc=2.5 dt=0.005   (configs[1], default at --gpus 1)
-  ap65536  all-pairs N=65,536 rc=2.5 dt=0.005   (configs[2], default at --gpus > 1)
+  ap4096   all-pairs N=4,096  rc=2.5 dt=0.005   (configs[1]; the default.  A step is a few us of
+                                                  work: it does not shard -> --gpus N runs N
+                                                  independent replicas, "weak" scaling)
+  ap65536  all-pairs N=65,536 rc=2.5 dt=0.005   (configs[2]; --gpus N shards it: atom decomposition)
   cells4m  cell-list N=4,194,304 rho=0.8 rc=2.5 (configs[3])
-  cells16m cell-list N=16,777,216               (configs[4])
+  cells16m cell-list N=16,777,216               (configs[4]; --gpus N shards it: row slabs + halos)
 
 The reference arm (--impl reference) times the CPU restatement of the reference's own
 verlet_step (two dense autodiff force evaluations per step, torch CPU, all host threads) on the
@@ -39,10 +41,10 @@ WORKLOADS = {
                      desc="2D LJ all-pairs N=4096 rc=2.5 dt=0.005"),
     "ap65536":  dict(N=65536, rc=2.5, dt=0.005, path="allpairs", md_steps=20,
                      desc="2D LJ all-pairs N=65536 rc=2.5 dt=0.005"),
-    "cells4m":  dict(N=4194304, rc=2.5, dt=0.005, path="cells", md_steps=50,
-                     desc="2D LJ cell-list N=4194304 rho=0.8 rc=2.5 dt=0.005"),
-    "cells16m": dict(N=16777216, rc=2.5, dt=0.005, path="cells", md_steps=20,
-                     desc="2D LJ cell-list N=16777216 rho=0.8 rc=2.5 dt=0.005"),
+    "cells4m":  dict(N=4194304, rc=2.5, dt=0.005, path="cells", md_steps=200, skin=0.5,
+                     desc="2D LJ cell-list N=4194304 rho=0.8 rc=2.5 dt=0.005 (skin 0.5)"),
+    "cells16m": dict(N=16777216, rc=2.5, dt=0.005, path="cells", md_steps=100, skin=0.5,
+                     desc="2D LJ cell-list N=16777216 rho=0.8 rc=2.5 dt=0.005 (skin 0.5)"),
 }
 FLOP_PER_PAIR_FORCE = 25.0      # SURVEY.md §8d (fixed for builder and judge)
 BYTES_PER_PARTICLE_STEP = 32.0  # read+write R,V as float2
@@ -201,7 +203,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
-    wl_name = args.workload or ("ap4096" if args.gpus == 1 else "ap65536")
+    wl_name = args.workload or "ap4096"
     wl = dict(WORKLOADS[wl_name])
     if args.md_steps:
         wl["md_steps"] = args.md_steps
@@ -230,15 +232,16 @@ def main():
     dist_arg = None
     parallelism = "single GPU"
     if world > 1:
-        # atom/slab decomposition inside the library when built; else independent replicas
-        try:
+        if N >= 16384:
+            # atom decomposition (all-pairs) / row slabs with halo exchange (cell list) inside the library
             from jax_tpus_benchmark_physics_simulation_b200.md import make_dist_arg
             dist_arg = make_dist_arg(rank, world)
             parallelism = f"sharded x{world}"
-        except Exception:
-            dist_arg = None
+        else:
+            # a step of this system is a few microseconds: it does not shard
             parallelism = f"replicas x{world}"
-    sim = LJSimulation(N, rc=rc, dt=dt, path=wl["path"], device=local_rank, dist=dist_arg)
+    sim = LJSimulation(N, rc=rc, dt=dt, path=wl["path"], device=local_rank, dist=dist_arg,
+                       skin=wl.get("skin", 0.3))
 
     # device-resident inputs for `value`
     Rd = torch.from_numpy(R).cuda()

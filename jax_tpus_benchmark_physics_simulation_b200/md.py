@@ -326,6 +326,19 @@ def slab_range(N: int, rank: int, nranks: int) -> Tuple[int, int]:
     return rank * n, (rank + 1) * n
 
 
+def row_slab_range(nrows: int, rank: int, nranks: int) -> Tuple[int, int]:
+    """Slab decomposition of the cell-list path: rank p owns the contiguous block of strip-cell
+    rows [g0, g0 + nloc), blocks as even as possible (the first nrows % P ranks own one more), and
+    holds one halo row on each side (csrc/cells.cu::cells_create).  Needs 2 rows per rank."""
+    if nranks < 1 or not (0 <= rank < nranks):
+        raise ValueError(f"bad rank {rank} / nranks {nranks}")
+    if nranks > 1 and nrows < 2 * nranks:
+        raise ValueError(f"{nrows} rows cannot be split over {nranks} ranks (need 2 rows per rank)")
+    base, extra = divmod(nrows, nranks)
+    g0 = rank * base + min(rank, extra)
+    return g0, base + (1 if rank < extra else 0)
+
+
 def broadcast_unique_id(rank: int, get_uid=None) -> bytes:
     """Rank 0 creates the 128-byte NCCL unique id (ljmd_get_unique_id) and broadcasts it over the
     already-initialised torch.distributed group (any backend: gloo on CPU, nccl on GPUs)."""

@@ -13,7 +13,7 @@ WORKER = r'''
 import os, sys
 sys.path.insert(0, os.environ["LJMD_ROOT"])
 import torch.distributed as dist
-from jax_tpus_benchmark_physics_simulation_b200.md import broadcast_unique_id, slab_range
+from jax_tpus_benchmark_physics_simulation_b200.md import broadcast_unique_id, slab_range, row_slab_range
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 uid = broadcast_unique_id(rank, get_uid=lambda: bytes(range(128)))
@@ -25,6 +25,14 @@ assert got[0][0] == 0 and got[-1][1] == 65536
 for a, b in zip(got[:-1], got[1:]):
     assert a[1] == b[0]
 assert all(h - l == 65536 // world for l, h in got)
+# row slabs of the cell-list path: contiguous, cover all rows, sizes differ by at most one
+g0, nloc = row_slab_range(1635, rank, world)
+rows = [None] * world
+dist.all_gather_object(rows, (g0, nloc))
+assert rows[0][0] == 0 and rows[-1][0] + rows[-1][1] == 1635
+for a, b in zip(rows[:-1], rows[1:]):
+    assert a[0] + a[1] == b[0]
+assert max(n for _, n in rows) - min(n for _, n in rows) <= 1
 dist.barrier()
 dist.destroy_process_group()
 print("OK", rank)

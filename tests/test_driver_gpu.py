@@ -42,3 +42,15 @@ def test_sharded_allpairs_matches_single_gpu():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("-> OK") == 2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_cells_matches_single_gpu():
+    """Row slabs + halo exchange over NVLink: forces, energies and a 60-step trajectory (several
+    rebuilds, particles migrating between slabs) equal the single-GPU cell-list run."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29543",
+           os.path.join(ROOT, "scripts", "dist_cells_check.py"), "65536", "60"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("-> OK") == 2
