@@ -124,8 +124,10 @@ int ljmd_last_rebuilds(ljmd_t* h, int64_t* rebuilds);
 /* ---- multi-GPU (new; the reference is single-device) ---------------------------- */
 /* One handle per rank/device.  nccl_unique_id: the 128 bytes of an ncclUniqueId made
  * by rank 0 and broadcast by the caller (e.g. over torch.distributed/gloo).
- * Atom decomposition for all-pairs (position all-gather each step), x-slab
- * decomposition with halo exchange for the cell list; one all-reduce for energies.
+ * Atom decomposition for all-pairs (position exchange each step), row-slab
+ * decomposition with halo-row exchange for the cell list (both as in-kernel NVLink peer
+ * stores); one all-reduce for energies.  Cell list on several GPUs: no thermostat, outputs
+ * must not alias inputs, neighbor_count is single-GPU.
  * R/V arguments of ljmd_run etc. are then the FULL (N,2) arrays on every rank
  * (replicated in, replicated out) so the Python closures keep their signatures.     */
 int ljmd_get_unique_id(void* id128);
