@@ -58,7 +58,11 @@ constexpr int CL_NW        = 16;    // byte-list words per particle (64 neighbou
 constexpr int CL_NWPRE     = 6;     // words requested before the loop (24 neighbours)
 constexpr int CL_BROW      = 4 * CL_NW + 4;   // a lane's byte row while a list is built (17 words:
                                               // rows of different lanes start in different banks)
-constexpr int CL_WARP_SMEM = CL_WSLOTS * 8 + 32 * CL_BROW;            // bytes per warp
+// per-warp shared memory: two window buffers (the per-step pass double-buffers them with cp.async)
+// and two word buffers (the first CL_NWPRE list words of every lane); the list build uses window
+// buffer 0 and lays its byte rows over the rest
+constexpr int CL_WARP_SMEM = 2 * CL_WSLOTS * 8 + 2 * CL_NWPRE * 32 * 4;  // bytes per warp
+static_assert(CL_WSLOTS * 8 + 32 * CL_BROW <= CL_WARP_SMEM, "byte rows must fit behind window buffer 0");
 constexpr int CL_WARPS     = CL_THREADS / 32;
 constexpr int CL_ORDER_MAX = 64;    // cells denser than this keep arrival order (see B5)
 
@@ -95,7 +99,7 @@ struct CellsArgs {
     uint2*    ent;
     unsigned* nb4;                  // byte lists of staged warps, ELL nb4[w * Nalloc + i]
     int4*     wplan;                // per warp of 32 slots: 2 x int4 (window starts / lengths, flag)
-    float  *pe_part, *ke_part;      // [2*nchunks] per-chunk partials (by step parity)
+    float  *pe_part, *ke_part;      // [2*nchunks] per-unit partials (by step parity); nchunks = unit capacity
     int*      sched;                // [2] chunk counters (by step parity)
     int*      state;                // ST_* words
     unsigned* bar;
@@ -672,6 +676,192 @@ __device__ __forceinline__ void bytes_force(const CellsArgs& a, const float2* wi
     if (PE) pe = pe2.x + pe2.y;
 }
 
+// ---- cp.async (LDGSTS) helpers: global -> shared without passing through registers ------------------
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// staged units: the list is one byte per neighbour (index into the staged windows), four per word,
+// padded with the sentinel index to the warp's longest list (nw words, warp-uniform); the first
+// CL_NWPRE words of every lane were copied to shared memory together with the windows
+template <bool PE>
+__device__ __forceinline__ void bytes_force_staged(const CellsArgs& a, const float2* win, const unsigned* sw,
+                                                   int i, int nw, float2 ri, float& Fx, float& Fy, float& pe) {
+    const PairConsts pc = a.pc;
+    const PairConsts2 c2 = make_pair_consts2(pc);
+    const int lane = threadIdx.x & 31;
+    const float2 nri = make_float2(-ri.x, -ri.y);
+    float2 acc = make_float2(0.0f, 0.0f), pe2 = acc;
+#pragma unroll
+    for (int u = 0; u < CL_NWPRE; ++u)
+        if (u < nw) word_eval<PE>(pc, c2, win, sw[u * 32 + lane], nri, acc, pe2);          // warp-uniform
+    for (int u = CL_NWPRE; u < nw; ++u)
+        word_eval<PE>(pc, c2, win, a.nb4[(size_t)u * a.Nalloc + i], nri, acc, pe2);
+    Fx = -acc.x;
+    Fy = -acc.y;
+    if (PE) pe = pe2.x + pe2.y;
+}
+
+struct StepFlags {
+    long long s;
+    int  par;
+    bool kick1, final, want_e, want_pe, want_ke, thermo, sample;
+};
+
+// ---- one step's pass of one warp --------------------------------------------------------------------
+// A unit = 32 consecutive slots = one warp.  Warp gw evaluates units u_lo + gw + k * W (interleaved:
+// every warp sees units of ~28 different rows, which evens out density and edge effects; warps never
+// wait for each other inside a step).  Software pipeline, driven by cp.async: while unit k is
+// evaluated out of one shared-memory buffer, the windows and list words of unit k+1 are streaming
+// into the other one and the copy plan of unit k+2 is on its way to registers.
+template <bool PE>
+__device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, const StepFlags& fl,
+                                          float2* wbuf /* [2][CL_WSLOTS] */, unsigned* swbuf /* [2][CL_NWPRE][32] */,
+                                          int& moved) {
+    const RunCtl& rc = a.rc;
+    const int lane = threadIdx.x & 31;
+    const int W = a.G * CL_WARPS, gw = blockIdx.x * CL_WARPS + (threadIdx.x >> 5);
+    const int u_lo = ctx.own_s >> 5, u_hi = (ctx.own_e + 31) >> 5;
+    const float2* __restrict__ R = a.R[ctx.pr];
+    float2* Rnext = a.R[ctx.pr ^ 1];
+    float2* V = a.V[ctx.pv];
+    const int* og = a.orig[ctx.pv];
+    // halo pushes (slabs): slots of my first / last owned row and where they live in the neighbours
+    const int dn = (a.me + a.P - 1) % a.P, up = (a.me + 1) % a.P;
+    int first_e = 0, last_s = 0, peer_hi_start = 0;
+    if (a.P > 1) {
+        first_e = a.cell_start[(a.own_lo + 1) * a.nbx];
+        last_s = a.cell_start[(a.own_lo + a.nloc - 1) * a.nbx];
+        peer_hi_start = __ldcg(&a.mail[MB_HI_START]);
+    }
+    // the sentinel slots behind the staged windows (never within rc of anything)
+    if (lane >= 28) {
+        wbuf[3 * CL_WIN + (lane & 3)] = make_float2(1.0e9f, 1.0e9f);
+        wbuf[CL_WSLOTS + 3 * CL_WIN + (lane & 3)] = make_float2(1.0e9f, 1.0e9f);
+    }
+    __syncwarp();
+
+    // copy plan of a unit: (ws0, ws1, ws2, staged) (wn0, wn1, wn2, nwords)
+    auto issue = [&](int u, const int4& p0, const int4& p1, int buf) {
+        if (u < u_hi && p0.w != 0) {
+            float2* win = wbuf + buf * CL_WSLOTS;
+            unsigned* sw = swbuf + buf * (CL_NWPRE * 32);
+#pragma unroll
+            for (int j = 0; j < CL_WIN; j += 32) {
+                if (j + lane < p1.x) cp_async8(win + j + lane, R + p0.x + j + lane);
+                if (j + lane < p1.y) cp_async8(win + CL_WIN + j + lane, R + p0.y + j + lane);
+                if (j + lane < p1.z) cp_async8(win + 2 * CL_WIN + j + lane, R + p0.z + j + lane);
+            }
+            const int i = u * 32 + lane;
+#pragma unroll
+            for (int w = 0; w < CL_NWPRE; ++w)
+                if (w < p1.w) cp_async4(sw + w * 32 + lane, a.nb4 + (size_t)w * a.Nalloc + i);
+        }
+        cp_async_commit();
+    };
+    // Schedule: the first ~70 % of the units statically interleaved (no traffic), the rest drawn one by
+    // one from a per-step counter: warps that met several slow (edge) units take fewer of the tail.
+    const int rounds0 = (int)(0.7f * (float)((u_hi - u_lo) / W));
+    const int dyn_lo = u_lo + rounds0 * W;
+    auto grab = [&](int j) -> int {                       // j-th unit of this warp (value valid in lane 0
+        if (j < rounds0) return u_lo + gw + j * W;        //  for the dynamic part: broadcast before use)
+        int t = 0;
+        if (lane == 0) t = dyn_lo + atomicAdd(&a.sched[fl.par], 1);
+        return t;
+    };
+    const int4 z4 = make_int4(0, 0, 0, 0);
+    int u = __shfl_sync(0xffffffffu, grab(0), 0), un = __shfl_sync(0xffffffffu, grab(1), 0);
+    int g = grab(2);                                      // drawn now, broadcast one unit later
+    int4 p0 = z4, p1 = z4, q0 = z4, q1 = z4;
+    if (u < u_hi) { p0 = a.wplan[2 * u]; p1 = a.wplan[2 * u + 1]; }
+    if (un < u_hi) { q0 = a.wplan[2 * un]; q1 = a.wplan[2 * un + 1]; }
+    issue(u, p0, p1, 0);
+
+    for (int k = 0; u < u_hi; ++k) {
+        const int buf = k & 1;
+        issue(un, q0, q1, buf ^ 1);                       // next unit's windows + words
+        const int unn = __shfl_sync(0xffffffffu, g, 0);
+        g = grab(k + 3);
+        int4 r0 = z4, r1 = z4;
+        if (unn < u_hi) { r0 = a.wplan[2 * unn]; r1 = a.wplan[2 * unn + 1]; }   // consumed next iteration
+        const int  i    = u * 32 + lane;
+        const bool live = (i >= ctx.own_s) & (i < ctx.own_e);
+        // epilogue operands requested now, consumed after the pair loop
+        float2 v = make_float2(0.0f, 0.0f), rb = make_float2(0.0f, 0.0f);
+        if (live && rc.nsteps > 0) { v = V[i]; rb = a.Rb[i]; }
+        float2 ri = make_float2(0.0f, 0.0f);
+        float Fx = 0.0f, Fy = 0.0f, pe = 0.0f, ke = 0.0f;
+        const int ii = live ? i : ctx.own_s;
+        cp_async_wait<1>();                               // this unit's copies have landed
+        __syncwarp();
+        if (p0.w != 0) {
+            const float2* win = wbuf + buf * CL_WSLOTS;
+            if (live) ri = win[CL_WIN + (i - p0.y)];      // own row window holds the own slot
+            bytes_force_staged<PE>(a, win, swbuf + buf * (CL_NWPRE * 32), ii, p1.w, ri, Fx, Fy, pe);
+        } else {
+            unsigned meta = 0u;
+            if (live) { ri = R[i]; meta = a.meta[i]; }
+            const int n = meta & 0xff;
+            const bool wedge = __any_sync(0xffffffffu, (meta & 0x100u) != 0u);
+            if (wedge) list_force<PE, true >(a, R, ii, n, ri, Fx, Fy, pe);
+            else       list_force<PE, false>(a, R, ii, n, ri, Fx, Fy, pe);
+        }
+        if (live) {
+            if (fl.kick1) { v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt); }            // MD:74
+            if (fl.want_ke) ke = v.x * v.x + v.y * v.y;
+            const int o = (fl.sample || (fl.final && !fl.thermo)) ? og[i] : 0;
+            if (fl.sample) rc.traj[(size_t)(fl.s / rc.sample_every) * a.N + o] = ri;           // MD:93-100
+            if (fl.thermo) {
+                V[i] = v;
+                a.Fs[i] = make_float2(Fx, Fy);
+            } else if (fl.final) {
+                if (a.R_out) a.R_out[o] = ri;
+                if (a.V_out) a.V_out[o] = v;
+                if (a.F_out) a.F_out[o] = make_float2(Fx, Fy);
+            } else {
+                v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt);                           // MD:70
+                V[i] = v;
+                const float2 rn = make_float2(drift(ri.x, v.x, a.dt, a.pc.box),                 // MD:71-72
+                                              drift(ri.y, v.y, a.dt, a.pc.box));
+                Rnext[i] = rn;
+                if (a.P > 1) {
+                    // halo exchange: the new position and velocity of a boundary-row particle go
+                    // straight into the neighbour's halo slot (NVLink peer store)
+                    if (i < first_e) {
+                        const int j = peer_hi_start + (i - ctx.own_s);
+                        a.peerR[ctx.pr ^ 1][dn][j] = rn; a.peerV[ctx.pv][dn][j] = v;
+                    }
+                    if (i >= last_s) {
+                        const int j = i - last_s;
+                        a.peerR[ctx.pr ^ 1][up][j] = rn; a.peerV[ctx.pv][up][j] = v;
+                    }
+                }
+                const float ddx = min_image(__fsub_rn(rn.x, rb.x), a.pc.box, a.pc.timg);
+                const float ddy = min_image(__fsub_rn(rn.y, rb.y), a.pc.box, a.pc.timg);
+                moved |= (ddx * ddx + ddy * ddy > a.half_skin2);
+            }
+        }
+        // per-unit energy partials (fixed shuffle tree), summed in unit order after the barrier
+        if (PE) {
+            const float t = warp_sum(pe);
+            if (lane == 0) __stcg(&a.pe_part[fl.par * a.nchunks + (u - u_lo)], t);
+        }
+        if (fl.want_ke) {
+            const float t = warp_sum(ke);
+            if (lane == 0) __stcg(&a.ke_part[fl.par * a.nchunks + (u - u_lo)], t);
+        }
+        __syncwarp();                                     // all lanes are done with `buf`
+        u = un; un = unn; p0 = q0; p1 = q1; q0 = r0; q1 = r1;
+    }
+    cp_async_wait<0>();
+}
+
 extern __shared__ __align__(16) unsigned char cells_smem[];
 
 __global__ void __launch_bounds__(CL_THREADS, 2)
@@ -681,7 +871,6 @@ cells_persistent_kernel(const CellsArgs a) {
     __shared__ double sdbl[CL_THREADS / 32];
     __shared__ float  s_lambda;
     __shared__ long long s_pt[12];
-    __shared__ int    s_ch[2][2];                       // (current, next) chunk, double-buffered
     const int tid = threadIdx.x, gtid = blockIdx.x * CL_THREADS + tid, gsz = a.G * CL_THREADS;
     const RunCtl rc = a.rc;
     Ctx ctx;
@@ -695,11 +884,11 @@ cells_persistent_kernel(const CellsArgs a) {
     ctx.own_e = a.state[ST_OWN_E];
     ctx.xepoch = (unsigned)a.state[ST_XEPOCH];
     // per warp: staged neighbour windows (+ sentinel slots) and the byte rows of the list build
+    // (window buffer 0 | window buffer 1 | word buffers; the list build lays its byte rows over
+    //  everything behind window buffer 0)
     float2* my_win = reinterpret_cast<float2*>(cells_smem + (size_t)(tid >> 5) * CL_WARP_SMEM);
     unsigned char* my_bytes = cells_smem + (size_t)(tid >> 5) * CL_WARP_SMEM + CL_WSLOTS * 8;
-    // the sentinel slots behind the staged windows (never within rc of anything; never overwritten)
-    if ((tid & 31) >= 28) my_win[3 * CL_WIN + (tid & 3)] = make_float2(1.0e9f, 1.0e9f);
-    __syncthreads();
+    unsigned* my_words = reinterpret_cast<unsigned*>(cells_smem + (size_t)(tid >> 5) * CL_WARP_SMEM + 2 * CL_WSLOTS * 8);
 
     if (a.s_begin < 0) {
         // load the caller's state (original order) and sort it.  Slabs: every rank reads the whole
@@ -759,130 +948,17 @@ cells_persistent_kernel(const CellsArgs a) {
         float2*       Rnext = a.R[ctx.pr ^ 1];
         float2*       V     = a.V[ctx.pv];
         const int*    og    = a.orig[ctx.pv];
-
-        // Chunks of CL_THREADS slots are handed out dynamically (one atomic per chunk, drawn two
-        // chunks ahead by thread 0): rows differ in density and edge warps are slower, a static
-        // split leaves CTAs idle at the barrier.  No result depends on which CTA ran a chunk.
-        if (gtid == 0) __stcg(&a.sched[par ^ 1], 0);     // the other parity's counter: idle this step
-        // chunks are aligned to multiples of CL_THREADS slots (the warp plans are per 32 aligned
-        // slots); the owned slot range may start and end inside a chunk
-        const int ch_lo = ctx.own_s / CL_THREADS, ch_hi = (ctx.own_e + CL_THREADS - 1) / CL_THREADS;
-        // halo pushes (slabs): slots of my first / last owned row and where they live in the neighbours
-        const int dn = (a.me + a.P - 1) % a.P, up = (a.me + 1) % a.P;
-        int first_e = 0, last_s = 0, peer_hi_start = 0;
-        if (a.P > 1) {
-            first_e = a.cell_start[(a.own_lo + 1) * a.nbx];
-            last_s = a.cell_start[(a.own_lo + a.nloc - 1) * a.nbx];
-            peer_hi_start = __ldcg(&a.mail[MB_HI_START]);
-        }
-        int c_cur = 0, c_nxt = 0;
-        if (tid == 0) { c_cur = ch_lo + atomicAdd(&a.sched[par], 1); c_nxt = ch_lo + atomicAdd(&a.sched[par], 1); }
+        StepFlags fl;
+        fl.s = s; fl.par = par; fl.kick1 = kick1; fl.final = final; fl.want_e = want_e; fl.want_pe = want_pe;
+        fl.want_ke = want_ke; fl.thermo = thermo; fl.sample = sample;
+        const int u_lo = ctx.own_s >> 5, u_hi = (ctx.own_e + 31) >> 5;      // 32-slot units
+        if (gtid == 0) __stcg(&a.sched[par ^ 1], 0);     // the other parity's unit counter: idle this step
         int moved = 0;
-        for (int it = 0;; ++it) {
-            if (tid == 0) { s_ch[it & 1][0] = c_cur; s_ch[it & 1][1] = c_nxt; }
-            __syncthreads();
-            const int ch = s_ch[it & 1][0], chn = s_ch[it & 1][1];
-            if (ch >= ch_hi) break;
-            if (tid == 0) { c_cur = c_nxt; c_nxt = ch_lo + atomicAdd(&a.sched[par], 1); }
-            const int  i    = ch * CL_THREADS + tid;
-            const bool live = (i >= ctx.own_s) & (i < ctx.own_e);
-            // The pass streams ~70 bytes per particle and a warp has one particle per lane in flight:
-            // without help the SM holds too few bytes in flight to cover the HBM latency.  Request the
-            // NEXT chunk's operands now (L2 -> L1 prefetch); they arrive while this chunk is evaluated.
-            {
-                const int inext = chn * CL_THREADS + tid;
-                if (inext < ctx.own_e) {
-                    prefetch_l1(R + inext);
-                    prefetch_l1(a.meta + inext);
-#pragma unroll
-                    for (int u = 0; u < CL_NWPRE; ++u) prefetch_l1(a.nb4 + (size_t)u * a.Nalloc + inext);
-                    if (rc.nsteps > 0) { prefetch_l1(V + inext); prefetch_l1(a.Rb + inext); }
-                    if ((tid & 31) == 0) prefetch_l1(a.wplan + 2 * (inext >> 5));
-                }
-            }
-            float2 ri = make_float2(0.0f, 0.0f);
-            unsigned meta = 0u;                         // dead lanes: interior, no neighbours
-            if (live) { ri = R[i]; meta = a.meta[i]; }
-            const int n = meta & 0xff;
-            const bool wedge = __any_sync(0xffffffffu, (meta & 0x100u) != 0u);
-            // epilogue operands requested now, consumed after the force loop
-            float2 v = make_float2(0.0f, 0.0f), rb = make_float2(0.0f, 0.0f);
-            if (live && rc.nsteps > 0) { v = V[i]; rb = a.Rb[i]; }
-            float Fx = 0.0f, Fy = 0.0f, pe = 0.0f, ke = 0.0f;
-            const int ii = live ? i : 0;
-            // the warp's three neighbour windows -> shared memory (coalesced), then LDS gathers
-            const int wid = i >> 5;
-            const int4 p0 = (wid * 32 < ctx.own_e && wid * 32 + 32 > ctx.own_s) ? a.wplan[2 * wid] : make_int4(0, 0, 0, 0);
-            const bool staged = p0.w != 0;
-            float2* win = my_win;
-            if (staged) {
-                const int4 p1 = a.wplan[2 * wid + 1];
-                const int lane = tid & 31;
-                __syncwarp();                                   // previous chunk's readers are done
-#pragma unroll
-                for (int j = 0; j < CL_WIN; j += 32) {
-                    if (j + lane < p1.x) win[j + lane] = R[p0.x + j + lane];
-                    if (j + lane < p1.y) win[CL_WIN + j + lane] = R[p0.y + j + lane];
-                    if (j + lane < p1.z) win[2 * CL_WIN + j + lane] = R[p0.z + j + lane];
-                }
-                __syncwarp();
-                if (want_pe) bytes_force<true >(a, win, ii, p1.w, ri, Fx, Fy, pe);
-                else         bytes_force<false>(a, win, ii, p1.w, ri, Fx, Fy, pe);
-            } else if (want_pe) {
-                if (wedge) list_force<true, true >(a, R, ii, n, ri, Fx, Fy, pe);
-                else       list_force<true, false>(a, R, ii, n, ri, Fx, Fy, pe);
-            } else {
-                if (wedge) list_force<false, true >(a, R, ii, n, ri, Fx, Fy, pe);
-                else       list_force<false, false>(a, R, ii, n, ri, Fx, Fy, pe);
-            }
-            if (live) {
-                if (kick1) { v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt); }            // MD:74
-                if (want_ke) ke = v.x * v.x + v.y * v.y;
-                const int o = (sample || (final && !thermo)) ? og[i] : 0;
-                if (sample) rc.traj[(size_t)(s / rc.sample_every) * a.N + o] = ri;              // MD:93-100
-                if (thermo) {
-                    V[i] = v;
-                    a.Fs[i] = make_float2(Fx, Fy);
-                } else if (final) {
-                    if (a.R_out) a.R_out[o] = ri;
-                    if (a.V_out) a.V_out[o] = v;
-                    if (a.F_out) a.F_out[o] = make_float2(Fx, Fy);
-                } else {
-                    v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt);                         // MD:70
-                    V[i] = v;
-                    const float2 rn = make_float2(drift(ri.x, v.x, a.dt, a.pc.box),               // MD:71-72
-                                                  drift(ri.y, v.y, a.dt, a.pc.box));
-                    Rnext[i] = rn;
-                    if (a.P > 1) {
-                        // halo exchange: the new position and velocity of a boundary-row particle go
-                        // straight into the neighbour's halo slot (NVLink peer store)
-                        if (i < first_e) {
-                            const int j = peer_hi_start + (i - ctx.own_s);
-                            a.peerR[ctx.pr ^ 1][dn][j] = rn; a.peerV[ctx.pv][dn][j] = v;
-                        }
-                        if (i >= last_s) {
-                            const int j = i - last_s;
-                            a.peerR[ctx.pr ^ 1][up][j] = rn; a.peerV[ctx.pv][up][j] = v;
-                        }
-                    }
-                    const float ddx = min_image(__fsub_rn(rn.x, rb.x), a.pc.box, a.pc.timg);
-                    const float ddy = min_image(__fsub_rn(rn.y, rb.y), a.pc.box, a.pc.timg);
-                    moved |= (ddx * ddx + ddy * ddy > a.half_skin2);
-                }
-            }
-            // per-chunk energy partials (fixed reduction tree), summed in chunk order after the barrier
-            if (want_pe) {
-                const float t = block_sum<CL_THREADS>(pe, sred);
-                if (tid == 0) __stcg(&a.pe_part[par * a.nchunks + ch], t);
-            }
-            if (want_ke) {
-                const float t = block_sum<CL_THREADS>(ke, sred);
-                if (tid == 0) __stcg(&a.ke_part[par * a.nchunks + ch], t);
-            }
-        }
+        if (want_pe) warp_pass<true >(a, ctx, fl, my_win, my_words, moved);
+        else         warp_pass<false>(a, ctx, fl, my_win, my_words, moved);
         if (thermo) {
             CL_BARRIER();
-            const double ke2 = block_sum_array(a.ke_part + par * a.nchunks + ch_lo, ch_hi - ch_lo, sdbl);
+            const double ke2 = block_sum_array(a.ke_part + par * a.nchunks, u_hi - u_lo, sdbl);
             if (tid == 0) s_lambda = sqrtf(rc.thermo_kT / ((float)(0.5 * ke2) / (float)a.N));
             __syncthreads();
             const float lam = s_lambda;
@@ -928,9 +1004,9 @@ cells_persistent_kernel(const CellsArgs a) {
         CL_PROF(1);
 
         if (blockIdx.x == 0 && want_pe) {
-            const double pe2 = block_sum_array(a.pe_part + par * a.nchunks + ch_lo, ch_hi - ch_lo, sdbl);
+            const double pe2 = block_sum_array(a.pe_part + par * a.nchunks, u_hi - u_lo, sdbl);
             double ke2 = 0.0;
-            if (want_e) ke2 = block_sum_array(a.ke_part + par * a.nchunks + ch_lo, ch_hi - ch_lo, sdbl);
+            if (want_e) ke2 = block_sum_array(a.ke_part + par * a.nchunks, u_hi - u_lo, sdbl);
             if (tid == 0) {
                 if (want_e) {
                     float* o = rc.ke_pe + 2 * (s / rc.energy_every);
@@ -1038,7 +1114,7 @@ int cells_create(ljmd_handle* h) {
         const double row = (double)N / cl->nrows;
         cl->Nalloc = (int)((((long long)(1.35 * per + 6.0 * row) + 4096 + 63) / 64) * 64);
     }
-    cl->nchunks = cl->Nalloc / CL_THREADS + 2;
+    cl->nchunks = cl->Nalloc / 32 + 2;              // capacity in 32-slot units (energy partials)
 
     const size_t smem = (size_t)CL_WARPS * CL_WARP_SMEM;
     LJ_CUDA(cudaFuncSetAttribute(cells_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
