@@ -43,7 +43,7 @@ WORKLOADS = {
                      desc="2D LJ all-pairs N=65536 rc=2.5 dt=0.005"),
     "cells4m":  dict(N=4194304, rc=2.5, dt=0.005, path="cells", md_steps=200, skin=0.5,
                      desc="2D LJ cell-list N=4194304 rho=0.8 rc=2.5 dt=0.005 (skin 0.5)"),
-    "cells16m": dict(N=16777216, rc=2.5, dt=0.005, path="cells", md_steps=100, skin=0.5,
+    "cells16m": dict(N=16777216, rc=2.5, dt=0.005, path="cells", md_steps=200, skin=0.5,
                      desc="2D LJ cell-list N=16777216 rho=0.8 rc=2.5 dt=0.005 (skin 0.5)"),
 }
 FLOP_PER_PAIR_FORCE = 25.0      # SURVEY.md §8d (fixed for builder and judge)
@@ -314,6 +314,13 @@ def main():
     h2d = Rh.numel() * 4 + Vh.numel() * 4
     d2h = Rh_out.numel() * 4 + Vh_out.numel() * 4 + E_out.numel() * 4
 
+    # one more run on EVERY rank (a sharded run is collective) for the per-launch kernel time
+    barrier()
+    sim.run(state, md_steps)
+    launch_ms = sim.last_run_ms()
+    rebuilds = sim.last_rebuilds() if wl["path"] == "cells" else 0
+    barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -323,8 +330,6 @@ def main():
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
     if wl["path"] == "allpairs":
         # persistent kernel: one launch = md_steps steps + the prologue force evaluation
-        sim.run(state, md_steps)
-        launch_ms = sim.last_run_ms()
         evals = md_steps + 1
         pairs = float(N) * float(N - 1) * evals / (world if sharded else 1)
         achieved = FLOP_PER_PAIR_FORCE * pairs / (launch_ms * 1e-3) / 1e12
@@ -342,16 +347,14 @@ def main():
                     "kernel": "ap_persistent_kernel", "flop_per_pair": FLOP_PER_PAIR_FORCE,
                     "pairs_per_launch": pairs, "launch_ms": launch_ms}
     else:
-        sim.run(state, md_steps)
-        launch_ms = sim.last_run_ms()
         bytes_ = BYTES_PER_PARTICLE_STEP * N * md_steps
         achieved = bytes_ / (launch_ms * 1e-3) / 1e9
-        peak = float(peaks["hbm_gbs"])
+        peak = float(peaks["hbm_gbs"]) * (world if sharded else 1)     # aggregate over the sharded GPUs
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None,
                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks_src})",
                     "bytes_per_particle_step": BYTES_PER_PARTICLE_STEP,
-                    "run_ms": launch_ms, "rebuilds": sim.last_rebuilds()}
+                    "run_ms": launch_ms, "rebuilds": rebuilds}
 
     # ---- CPU baseline: bounded sample of the same workload on this box's host cores ------------
     cpu_baseline = None

@@ -617,6 +617,7 @@ int ap_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_out
         const long long e = std::min(s_last, s + chunk);
         a.s_begin = s; a.s_end = e;
         a.xepoch0 = ap->xepoch;
+        if (a.P > 1) { int rb = dist_barrier(h); if (rb) return rb; }   // the ranks enter the kernel together
         LJ_CUDA(cudaMemsetAsync(ap->bar, 0, sizeof(unsigned), st));
         void* args[] = {(void*)&a};
         LJ_CUDA(cudaLaunchCooperativeKernel((void*)ap->kernel, dim3(ap->G), dim3(AP_THREADS), args, 0, st));

@@ -54,7 +54,7 @@ constexpr int CL_WIN       = 84;    // staged window capacity per stencil row an
                                     // 3 * CL_WIN = 252 slots fit a one-byte neighbour index
 constexpr int CL_WSLOTS    = 256;   // a warp's staging buffer: three windows + 4 sentinel slots
 constexpr int CL_DUMMY     = 255;   // byte index of a sentinel slot (pads the byte lists)
-constexpr int CL_NW        = 16;    // byte-list words per particle (64 neighbours)
+constexpr int CL_NW        = 24;    // byte-list words per particle (96 neighbours)
 constexpr int CL_NWPRE     = 6;     // words requested before the loop (24 neighbours)
 constexpr int CL_BROW      = 4 * CL_NW + 4;   // a lane's byte row while a list is built (17 words:
                                               // rows of different lanes start in different banks)
@@ -1268,6 +1268,7 @@ int cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_
     while (s < rc.nsteps) {
         const long long e = std::min(rc.nsteps, s + chunk);
         a.s_begin = s; a.s_end = std::max<long long>(e, 0);
+        if (P > 1) { int rb = dist_barrier(h); if (rb) return rb; }   // the ranks enter the kernel together
         int r = launch(h, a);
         if (r) return r;
         s = a.s_end;

@@ -68,6 +68,7 @@ int load_nccl() {
 
 struct Dist {
     ncclComm_t comm = nullptr;
+    float* scratch = nullptr;       // one float: payload of the stream barrier
     void* peer_mapped[LJMD_MAX_RANKS] = {};
     int n_mapped = 0;
 };
@@ -80,6 +81,19 @@ int dist_init(ljmd_handle* h, const void* nccl_unique_id) {
     ncclUniqueId id;
     memcpy(&id, nccl_unique_id, sizeof(id));
     LJ_NCCL(g_nccl.CommInitRank(&d->comm, h->nranks, id, h->rank));
+    LJ_CUDA(cudaMalloc(&d->scratch, sizeof(float)));
+    LJ_CUDA(cudaMemset(d->scratch, 0, sizeof(float)));
+    return 0;
+}
+
+// Cross-rank barrier IN STREAM ORDER (a one-float all-reduce): whatever a rank enqueues after it
+// starts only when every rank has reached this point of its stream.  The persistent kernels spin
+// on words their peers write, with a bail-out timer: the ranks have to enter them together even
+// if their host threads are seconds apart.
+int dist_barrier(ljmd_handle* h) {
+    Dist* d = h->dist;
+    if (!d) return 0;
+    LJ_NCCL(g_nccl.AllReduce(d->scratch, d->scratch, 1, ncclFloat32, ncclSum, d->comm, h->stream));
     return 0;
 }
 
@@ -88,6 +102,7 @@ void dist_destroy(ljmd_handle* h) {
     if (!d) return;
     for (int q = 0; q < LJMD_MAX_RANKS; ++q)
         if (d->peer_mapped[q]) cudaIpcCloseMemHandle(d->peer_mapped[q]);
+    if (d->scratch) cudaFree(d->scratch);
     if (d->comm) g_nccl.CommDestroy(d->comm);
     delete d;
     h->dist = nullptr;

@@ -111,6 +111,7 @@ void dist_destroy(ljmd_handle* h);
 int  dist_share(ljmd_handle* h, void* local_base, void** peer_bases /*[nranks]*/);
 int  dist_allgather(ljmd_handle* h, void* buf, size_t bytes_per_rank);   // in place, slab `rank`
 int  dist_allreduce_f32(ljmd_handle* h, float* buf, size_t n);
+int  dist_barrier(ljmd_handle* h);                      // cross-rank barrier in stream order
 
 // probe.cu
 int  fp32_peak_probe(int device, int packed, float* tflops);

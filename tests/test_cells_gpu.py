@@ -187,3 +187,31 @@ def test_full_size_config4_properties(oracle):
     assert sim.last_rebuilds() >= 2
     pos = R1.numpy()
     assert pos.min() >= 0.0 and pos.max() <= float(box)
+
+
+@pytest.mark.parametrize("rho,rc,kind", [(0.8, 2.5, "uniform"), (0.05, 2.5, "uniform"), (1.1, 2.5, "soft"),
+                                           (0.8, 3.5, "soft")])
+def test_non_lattice_inputs_vs_oracle(oracle, rho, rc, kind):
+    """Inputs that are not lattice-like: uniform random positions (the reference's own IC style,
+    MD:133: overlapping particles, |F| up to 1e30), sparse and dense systems, a longer cutoff.
+    Forces against the C cell-grid oracle and the all-pairs kernel; neighbour counts bit-exact."""
+    from jax_tpus_benchmark_physics_simulation_b200.ic import box_size
+    N = 16384
+    rng = np.random.default_rng(7)
+    box = box_size(N, rho)
+    if kind == "uniform":
+        R = (rng.random((N, 2)) * float(box)).astype(np.float32)
+    else:
+        n = int(round(np.sqrt(N))); a = float(box) / n
+        g = (np.stack(np.meshgrid(np.arange(n), np.arange(n), indexing="ij"), -1).reshape(-1, 2) + 0.5) * a
+        R = np.mod(g + rng.uniform(-0.3, 0.3, g.shape) * a, float(box)).astype(np.float32)
+    sim = _sim(N, rho=rho, rc=rc)
+    F = sim.force_fn(R).numpy()
+    Fo, _ = oracle.c_forces_cells(R, box, rc)
+    Fa = _sim(N, rho=rho, rc=rc, path="allpairs").force_fn(R).numpy()
+    fin = np.isfinite(Fo).all(axis=1) & np.isfinite(Fa).all(axis=1)
+    scale = np.abs(Fo[fin]).max()
+    assert np.abs(F[fin] - Fo[fin]).max() / scale <= FORCE_TOL
+    assert np.abs(F[fin] - Fa[fin]).max() / scale <= FORCE_TOL
+    got = sim.neighbor_count(R, rc).cpu().numpy()
+    assert np.array_equal(got, oracle.c_neighbor_count(R, box, rc))
