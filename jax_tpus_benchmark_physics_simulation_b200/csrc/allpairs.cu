@@ -61,6 +61,12 @@ struct ApArgs {
     float2*          Vh;          // velocities (half-step between kernels' phases)
     float2*          Ftmp;        // forces held across the thermostat barrier
     float2*          part;        // [G*maxseg*BLOCK_I] partial forces
+    // Newton's-third-law tile mode (IPT == 3): upper-triangular patches of Pt x Pt tiles of 64 x 64
+    int              Pt, q, npr;  // patch edge in tiles, tiles per warp edge (Pt = 2q), patch rows
+    const int*       cta_pstart;  // [G+1] range of `patches` owned by each CTA
+    const int2*      patches;     // (pa, pb) patch coordinates, pa <= pb
+    float2*          rowpart;     // [npatch][Pt*64] partial force on the patch's row (i) side
+    float2*          colpart;     // [npatch][Pt*64] partial force on the patch's column (j) side
     float*           pe_part;     // [2*G] per-CTA partial potential energy (by step parity)
     float*           ke_part;     // [2*G]
     unsigned*        bar;
@@ -163,6 +169,133 @@ __device__ __forceinline__ void ap_segment(const ApArgs& a, const float2* __rest
     }
 }
 
+// ---- Newton's-third-law tiles -------------------------------------------------------------------
+// A tile is 64 i-particles (two per lane, packed) x 32 j-particles (one per lane).  The j particle
+// and the force accumulated ON it travel around the warp by shuffle: after 32 steps every j has met
+// every lane's two i and is back in its home lane, so each unordered pair is evaluated once and
+// applied to both sides with no atomics and a fixed summation order.
+constexpr int T3_BLK = 64;
+
+__device__ __forceinline__ int tri_base(int pa, int npr) { return pa * npr - (pa * (pa - 1)) / 2; }
+
+template <bool CUTOFF, bool PE, bool N3L>
+__device__ __forceinline__ void tile_half(const PairConsts& pc, const PairConsts2& pc2, float2 xi2,
+                                          float2 yi2, float xj, float yj, bool self0, bool self1,
+                                          float2& fx2, float2& fy2, float2& pe2, float& fjx, float& fjy) {
+    const int src = (threadIdx.x + 1) & 31;
+    // the reaction on the travelling j is accumulated as ONE scalar per component (the two i of this
+    // lane are added in a fixed order), so only two values per component... per step two shuffles
+    // move (xj, yj) and two move the accumulators
+    float ajx = 0.0f, ajy = 0.0f;
+    // step 0 peeled: the only step at which j can be one of this lane's own i (diagonal tiles)
+    {
+        float2 f, dx, dy;
+        if (N3L) pair2_eval<CUTOFF, PE, false>(xi2, yi2, xj, yj, true, true, pc, pc2, f, dx, dy, pe2);
+        else     pair2_eval<CUTOFF, PE, true >(xi2, yi2, xj, yj, !self0, !self1, pc, pc2, f, dx, dy, pe2);
+        fx2 = __ffma2_rn(f, dx, fx2);
+        fy2 = __ffma2_rn(f, dy, fy2);
+        if (N3L) {
+            ajx = fmaf(f.y, dx.y, __fmul_rn(f.x, dx.x));
+            ajy = fmaf(f.y, dy.y, __fmul_rn(f.x, dy.x));
+        }
+        xj = __shfl_sync(0xffffffffu, xj, src);
+        yj = __shfl_sync(0xffffffffu, yj, src);
+        if (N3L) { ajx = __shfl_sync(0xffffffffu, ajx, src); ajy = __shfl_sync(0xffffffffu, ajy, src); }
+    }
+#pragma unroll 4
+    for (int s = 1; s < 32; ++s) {
+        float2 f, dx, dy;
+        pair2_eval<CUTOFF, PE, false>(xi2, yi2, xj, yj, true, true, pc, pc2, f, dx, dy, pe2);
+        fx2 = __ffma2_rn(f, dx, fx2);
+        fy2 = __ffma2_rn(f, dy, fy2);
+        if (N3L) {
+            ajx = fmaf(f.y, dx.y, fmaf(f.x, dx.x, ajx));
+            ajy = fmaf(f.y, dy.y, fmaf(f.x, dy.x, ajy));
+        }
+        xj = __shfl_sync(0xffffffffu, xj, src);
+        yj = __shfl_sync(0xffffffffu, yj, src);
+        if (N3L) { ajx = __shfl_sync(0xffffffffu, ajx, src); ajy = __shfl_sync(0xffffffffu, ajy, src); }
+    }
+    // 32 rotations: the travelling j (and its accumulator) is home again
+    fjx = -ajx;
+    fjy = -ajy;
+}
+
+__device__ __forceinline__ float2 ld_pos(const float2* __restrict__ R, int j, int N, float sent) {
+    return (j < N) ? __ldcg(&R[j]) : make_float2(sent, sent);
+}
+
+template <bool CUTOFF, bool PE>
+__device__ __forceinline__ void ap3_phase_forces(const ApArgs& a, const float2* __restrict__ Rcur,
+                                                 float2* sacc /* 4 warps x 2 x q x 64 */, float* sred,
+                                                 int par) {
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int wr = w >> 1, wc = w & 1, q = a.q, Pt = a.Pt;
+    const PairConsts pc = a.pc;
+    const PairConsts2 pc2 = make_pair_consts2(pc);
+    float2* rowacc = sacc + (size_t)w * 2 * q * T3_BLK;        // this warp's [q][64] row-side sums
+    float2* colacc = rowacc + (size_t)q * T3_BLK;              //             [q][64] column-side sums
+    float pe_thread = 0.0f;
+    for (int pi = a.cta_pstart[c]; pi < a.cta_pstart[c + 1]; ++pi) {
+        const int2 pp = a.patches[pi];
+        const int pid = tri_base(pp.x, a.npr) + (pp.y - pp.x);
+        for (int k = lane; k < q * T3_BLK; k += 32) colacc[k] = make_float2(0.0f, 0.0f);
+        __syncwarp();
+        for (int r = 0; r < q; ++r) {
+            const int ba = pp.x * Pt + wr * q + r;              // i block
+            const int i0 = ba * T3_BLK + lane, i1 = i0 + 32;
+            const float2 p0 = ld_pos(Rcur, i0, a.N, SENT_I), p1 = ld_pos(Rcur, i1, a.N, SENT_I);
+            const float2 xi2 = make_float2(p0.x, p1.x), yi2 = make_float2(p0.y, p1.y);
+            float2 fx2 = make_float2(0.0f, 0.0f), fy2 = fx2;
+            for (int cc = 0; cc < q; ++cc) {
+                const int bb = pp.y * Pt + wc * q + cc;         // j block
+                if (ba > bb) continue;                          // lower triangle (diagonal patches only)
+                float2 pe2 = make_float2(0.0f, 0.0f);
+                float2 tfx = make_float2(0.0f, 0.0f), tfy = tfx;   // per-tile sums (bounded chains)
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    const int j = bb * T3_BLK + h * 32 + lane;
+                    const float2 pj = ld_pos(Rcur, j, a.N, SENT_J);
+                    float fjx, fjy;
+                    if (ba < bb) {
+                        tile_half<CUTOFF, PE, true>(pc, pc2, xi2, yi2, pj.x, pj.y, false, false, tfx, tfy, pe2, fjx, fjy);
+                        float2 acc = colacc[cc * T3_BLK + h * 32 + lane];
+                        acc.x += fjx; acc.y += fjy;
+                        colacc[cc * T3_BLK + h * 32 + lane] = acc;
+                    } else {
+                        tile_half<CUTOFF, PE, false>(pc, pc2, xi2, yi2, pj.x, pj.y, h == 0, h == 1, tfx, tfy, pe2, fjx, fjy);
+                    }
+                }
+                fx2.x += tfx.x; fx2.y += tfx.y; fy2.x += tfy.x; fy2.y += tfy.y;
+                // energy bookkeeping in the ORDERED-pair convention of the caller (0.5 * sum):
+                // an unordered pair of an off-diagonal tile counts twice, a diagonal tile is ordered
+                if (PE) pe_thread += (ba < bb ? 2.0f : 1.0f) * (pe2.x + pe2.y);
+            }
+            rowacc[r * T3_BLK + lane]      = make_float2(fx2.x, fy2.x);
+            rowacc[r * T3_BLK + 32 + lane] = make_float2(fx2.y, fy2.y);
+        }
+        __syncthreads();
+        // combine the two warps that share a patch row / column (fixed order) -> global partials
+        float2* rp = a.rowpart + (size_t)pid * Pt * T3_BLK;
+        float2* cp = a.colpart + (size_t)pid * Pt * T3_BLK;
+        for (int k = tid; k < Pt * T3_BLK; k += AP_THREADS) {
+            const int blk = k / T3_BLK, off = k - blk * T3_BLK;
+            const int g2 = blk / q, rr = blk - g2 * q;          // warp-grid coordinate, tile within warp
+            const float2* ra0 = sacc + (size_t)(g2 * 2 + 0) * 2 * q * T3_BLK + rr * T3_BLK + off;          // wr=g2, wc=0
+            const float2* ra1 = sacc + (size_t)(g2 * 2 + 1) * 2 * q * T3_BLK + rr * T3_BLK + off;          // wr=g2, wc=1
+            const float2* ca0 = sacc + (size_t)(0 * 2 + g2) * 2 * q * T3_BLK + (q + rr) * T3_BLK + off;    // wr=0, wc=g2
+            const float2* ca1 = sacc + (size_t)(1 * 2 + g2) * 2 * q * T3_BLK + (q + rr) * T3_BLK + off;    // wr=1, wc=g2
+            __stcg(&rp[k], make_float2(ra0->x + ra1->x, ra0->y + ra1->y));
+            __stcg(&cp[k], make_float2(ca0->x + ca1->x, ca0->y + ca1->y));
+        }
+        __syncthreads();
+    }
+    if (PE) {
+        float t = block_sum<AP_THREADS>(pe_thread, sred);
+        if (tid == 0) __stcg(&a.pe_part[par * a.G + c], t);
+    }
+}
+
 template <int IPT, bool CUTOFF, bool PE>
 __device__ __forceinline__ void ap_phase_forces(const ApArgs& a, const float2* __restrict__ Rcur,
                                                 float4* sj, float* sred, int par) {
@@ -200,8 +333,10 @@ __device__ __forceinline__ double warp_sum_array(const float* p, int n) {
 template <int IPT, bool CUTOFF>
 __global__ void __launch_bounds__(AP_THREADS, AP_MINBLOCKS)
 ap_persistent_kernel(const ApArgs a) {
-    constexpr int BI = AP_THREADS * IPT;
-    __shared__ float4 sj[TILE_J];
+    constexpr int BI = AP_THREADS * (IPT == 3 ? 1 : IPT);
+    constexpr bool V3 = (IPT == 3);
+    __shared__ float4 smem_buf[V3 ? 2048 : TILE_J];          // v2: j tile; v3: per-warp tile sums (32 KB)
+    float4* sj = smem_buf;
     __shared__ float  sred[AP_THREADS / 32];
     __shared__ float  s_lambda;
     const int c = blockIdx.x, tid = threadIdx.x;
@@ -226,8 +361,13 @@ ap_persistent_kernel(const ApArgs a) {
 
         if (prof) pt[4] = clock64();
         // ---- [b] partial forces of R_cur ------------------------------------------------------
-        if (want_pe) ap_phase_forces<IPT, CUTOFF, true >(a, Rcur, sj, sred, par);
-        else         ap_phase_forces<IPT, CUTOFF, false>(a, Rcur, sj, sred, par);
+        if constexpr (V3) {
+            if (want_pe) ap3_phase_forces<CUTOFF, true >(a, Rcur, reinterpret_cast<float2*>(smem_buf), sred, par);
+            else         ap3_phase_forces<CUTOFF, false>(a, Rcur, reinterpret_cast<float2*>(smem_buf), sred, par);
+        } else {
+            if (want_pe) ap_phase_forces<IPT, CUTOFF, true >(a, Rcur, sj, sred, par);
+            else         ap_phase_forces<IPT, CUTOFF, false>(a, Rcur, sj, sred, par);
+        }
         if (prof) { long long t = clock64(); pt[0] += t - pt[4]; pt[4] = t; }
         grid_barrier(a.bar, (++epoch) * (unsigned)a.G, a.err);
         if (prof) { long long t = clock64(); pt[1] += t - pt[4]; pt[4] = t; }
@@ -250,13 +390,28 @@ ap_persistent_kernel(const ApArgs a) {
                 if (rc.nsteps > 0) v = a.Vh[g];
             }
             if (live) {
-                const int ib = gloc / BI, il = gloc - ib * BI;
-                const int2 cc = a.iblk_ctas[ib];
+                if constexpr (V3) {
+                    // row-side partials of patches (pr, pb >= pr), then column-side of (pa <= pr, pr)
+                    const int blk = g / T3_BLK, pr = blk / a.Pt;
+                    const size_t off = (size_t)(blk - pr * a.Pt) * T3_BLK + (g - blk * T3_BLK);
+                    const size_t pstride = (size_t)a.Pt * T3_BLK;
+                    const int n1 = a.npr - pr, ntot = n1 + pr + 1;
 #pragma unroll 4
-                for (int c2 = cc.x + gl; c2 <= cc.y; c2 += RED_LANES) {
-                    const int seg = ib - a.cta_ib0[c2];
-                    const float2 p = __ldcg(&a.part[((size_t)c2 * a.maxseg + seg) * BI + il]);
-                    Fx += p.x; Fy += p.y;
+                    for (int t = gl; t < ntot; t += RED_LANES) {
+                        float2 p;
+                        if (t < n1) p = __ldcg(&a.rowpart[(size_t)(tri_base(pr, a.npr) + t) * pstride + off]);
+                        else { const int pa = t - n1; p = __ldcg(&a.colpart[(size_t)(tri_base(pa, a.npr) + (pr - pa)) * pstride + off]); }
+                        Fx += p.x; Fy += p.y;
+                    }
+                } else {
+                    const int ib = gloc / BI, il = gloc - ib * BI;
+                    const int2 cc = a.iblk_ctas[ib];
+#pragma unroll 4
+                    for (int c2 = cc.x + gl; c2 <= cc.y; c2 += RED_LANES) {
+                        const int seg = ib - a.cta_ib0[c2];
+                        const float2 p = __ldcg(&a.part[((size_t)c2 * a.maxseg + seg) * BI + il]);
+                        Fx += p.x; Fy += p.y;
+                    }
                 }
             }
 #pragma unroll
@@ -375,6 +530,7 @@ ap_persistent_kernel(const ApArgs a) {
 using ApKernel = void (*)(const ApArgs);
 
 ApKernel pick_kernel(int ipt, bool cutoff) {
+    if (ipt == 3) return cutoff ? ap_persistent_kernel<3, true> : ap_persistent_kernel<3, false>;
     if (ipt == 1) return cutoff ? ap_persistent_kernel<1, true> : ap_persistent_kernel<1, false>;
     return cutoff ? ap_persistent_kernel<2, true> : ap_persistent_kernel<2, false>;
 }
@@ -435,6 +591,10 @@ gr_hist_kernel(const float2* __restrict__ Rh, int N, float box, float timg, int 
 // ----------------------------------------------------------------------------------------------
 struct AllPairs {
     int ipt = 1, G = 0, NJu = 0, nI = 0, maxseg = 0;
+    int Pt = 0, q = 0, npr = 0;                     // Newton's-third-law tile mode (ipt == 3)
+    int*  d_cta_pstart = nullptr;
+    int2* d_patches = nullptr;
+    float2 *rowpart = nullptr, *colpart = nullptr;
     long long* d_cta_start = nullptr;
     int*       d_cta_ib0 = nullptr;
     int2*      d_iblk = nullptr;
@@ -457,10 +617,12 @@ int ap_create(ljmd_handle* h) {
     AllPairs* ap = new AllPairs();
     h->ap = ap;
     const long long N = h->p.N;
-    ap->ipt = (N >= 2048) ? 2 : 1;
-    if (const char* e = getenv("LJMD_AP_IPT")) ap->ipt = (atoi(e) == 2) ? 2 : 1;
-    const int BI = AP_THREADS * ap->ipt;
     const int P = std::max(1, h->nranks);
+    // ipt 1 / 2: ordered pairs, one / two i per thread (stream-K split, any rank count);
+    // ipt 3: Newton's-third-law tiles (each unordered pair once, single GPU)
+    ap->ipt = (N >= 2048) ? ((P == 1) ? 3 : 2) : 1;
+    if (const char* e = getenv("LJMD_AP_IPT")) { const int v = atoi(e); if (v >= 1 && v <= 3 && (v != 3 || P == 1)) ap->ipt = v; }
+    const int BI = AP_THREADS * (ap->ipt == 3 ? 1 : ap->ipt);
     if (N % P != 0) { set_error("all-pairs atom decomposition needs N divisible by the rank count"); return LJMD_E_INVALID; }
     ap->Nloc = (int)(N / P);
     ap->i_lo = h->rank * ap->Nloc;
@@ -479,6 +641,30 @@ int ap_create(ljmd_handle* h) {
     long long g_work = std::max<long long>(1, W / (64 / J_UNIT));
     ap->G = (int)std::min<long long>((long long)per_sm * h->num_sms, std::min(g_work, W));
     if (const char* e = getenv("LJMD_AP_GRID")) ap->G = std::max(1, std::min(atoi(e), ap->G));
+    std::vector<int> pstart;
+    std::vector<int2> patches;
+    if (ap->ipt == 3) {
+        // upper-triangular patches of Pt x Pt tiles (tile = 64 x 64 particles); a CTA's 2 x 2 warps take
+        // q x q tiles each (Pt = 2q).  A diagonal patch does half the work of an off-diagonal one but
+        // takes the same time (its busiest warp has q*q tiles), so patches are dealt out evenly.
+        const int blocks = (int)((N + T3_BLK - 1) / T3_BLK);
+        const long long slots = (long long)per_sm * h->num_sms;
+        int q = 8;
+        for (; q > 1; q >>= 1) {
+            const long long npr = (blocks + 2 * q - 1) / (2 * q);
+            if (npr * (npr + 1) / 2 >= 4 * slots) break;          // enough patches to balance
+        }
+        if (const char* e = getenv("LJMD_AP_Q")) q = std::max(1, std::min(8, atoi(e)));
+        ap->q = q; ap->Pt = 2 * q;
+        ap->npr = (blocks + ap->Pt - 1) / ap->Pt;
+        for (int pa = 0; pa < ap->npr; ++pa)
+            for (int pb = pa; pb < ap->npr; ++pb) patches.push_back(make_int2(pa, pb));
+        const long long npatch = (long long)patches.size();
+        ap->G = (int)std::min<long long>(slots, npatch);
+        if (const char* e = getenv("LJMD_AP_GRID")) ap->G = std::max(1, std::min(atoi(e), ap->G));
+        pstart.resize(ap->G + 1);
+        for (int c = 0; c <= ap->G; ++c) pstart[c] = (int)(npatch * c / ap->G);
+    }
 
     // stream-K split of the flattened (i-block, j-unit) space, by COST: a j unit that overlaps
     // its own i-block runs the index-tested loop (~16% more instructions), so it weighs more.
@@ -560,6 +746,15 @@ int ap_create(ljmd_handle* h) {
     LJ_CUDA(cudaMalloc(&ap->Vh, sizeof(float2) * N));
     LJ_CUDA(cudaMalloc(&ap->Ftmp, sizeof(float2) * N));
     LJ_CUDA(cudaMalloc(&ap->part, sizeof(float2) * (size_t)ap->G * ap->maxseg * BI));
+    if (ap->ipt == 3) {
+        const size_t np = patches.size(), ps = (size_t)ap->Pt * T3_BLK;
+        LJ_CUDA(cudaMalloc(&ap->d_cta_pstart, sizeof(int) * pstart.size()));
+        LJ_CUDA(cudaMalloc(&ap->d_patches, sizeof(int2) * np));
+        LJ_CUDA(cudaMemcpy(ap->d_cta_pstart, pstart.data(), sizeof(int) * pstart.size(), cudaMemcpyHostToDevice));
+        LJ_CUDA(cudaMemcpy(ap->d_patches, patches.data(), sizeof(int2) * np, cudaMemcpyHostToDevice));
+        LJ_CUDA(cudaMalloc(&ap->rowpart, sizeof(float2) * np * ps));
+        LJ_CUDA(cudaMalloc(&ap->colpart, sizeof(float2) * np * ps));
+    }
     LJ_CUDA(cudaMalloc(&ap->pe_part, sizeof(float) * 2 * ap->G));
     LJ_CUDA(cudaMalloc(&ap->ke_part, sizeof(float) * 2 * ap->G));
     LJ_CUDA(cudaMalloc(&ap->bar, sizeof(unsigned)));
@@ -575,6 +770,7 @@ void ap_destroy(ljmd_handle* h) {
     cudaFree(ap->d_cta_start); cudaFree(ap->d_cta_ib0); cudaFree(ap->d_iblk);
     cudaFree(ap->shared); cudaFree(ap->Vh); cudaFree(ap->Ftmp);
     cudaFree(ap->part); cudaFree(ap->pe_part); cudaFree(ap->ke_part);
+    cudaFree(ap->d_cta_pstart); cudaFree(ap->d_patches); cudaFree(ap->rowpart); cudaFree(ap->colpart);
     cudaFree(ap->bar); cudaFree(ap->err);
     delete ap;
     h->ap = nullptr;
@@ -601,6 +797,8 @@ int ap_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_out
     a.cta_start = ap->d_cta_start; a.cta_ib0 = ap->d_cta_ib0; a.iblk_ctas = ap->d_iblk;
     a.R_in = R_in; a.Rbuf0 = ap->Rbuf0; a.Rbuf1 = ap->Rbuf1; a.Vh = ap->Vh; a.Ftmp = ap->Ftmp;
     a.part = ap->part; a.pe_part = ap->pe_part; a.ke_part = ap->ke_part;
+    a.Pt = ap->Pt; a.q = ap->q; a.npr = ap->npr;
+    a.cta_pstart = ap->d_cta_pstart; a.patches = ap->d_patches; a.rowpart = ap->rowpart; a.colpart = ap->colpart;
     a.bar = ap->bar; a.err = ap->err; a.prof = ap->prof;
     a.rc = rc;
     a.R_out = R_out; a.V_out = V_out; a.F_out = F_out; a.pe_out = pe_out;

@@ -107,6 +107,35 @@ __device__ __forceinline__ void pair2_accum(float2 xi2, float2 yi2, float2 nxj2,
     if (PE) pe2 = __ffma2_rn(ir6, __ffma2_rn(ir6, c2.d12, c2.nd6), pe2);
 }
 
+// Packed evaluation of the two pairs (i0 <- j), (i1 <- j) against ONE j (broadcast): returns the
+// force scalars f2 and the displacements so that the caller can apply the term to BOTH sides
+// (Newton's third law: f_ji = -f_ij bit for bit, because the min-image and r2 are symmetric).
+template <bool CUTOFF, bool PE, bool KEEPTEST>
+__device__ __forceinline__ void pair2_eval(float2 xi2, float2 yi2, float xj, float yj, bool keep0,
+                                           bool keep1, const PairConsts& c, const PairConsts2& c2,
+                                           float2& f, float2& dx, float2& dy, float2& pe2) {
+    dx = __fadd2_rn(xi2, make_float2(-xj, -xj));
+    dy = __fadd2_rn(yi2, make_float2(-yj, -yj));
+    dx.x = min_image(dx.x, c.box, c.timg);
+    dx.y = min_image(dx.y, c.box, c.timg);
+    dy.x = min_image(dy.x, c.box, c.timg);
+    dy.y = min_image(dy.y, c.box, c.timg);
+    const float2 r2 = __ffma2_rn(__fmul2_rn(dx, dx), c2.one, __fmul2_rn(dy, dy));   // unfused sum
+    float2 ir2 = make_float2(rcp_approx(r2.x), rcp_approx(r2.y));
+    if (CUTOFF) {
+        const bool in0 = KEEPTEST ? (keep0 & (r2.x < c.rc2)) : (r2.x < c.rc2);
+        const bool in1 = KEEPTEST ? (keep1 & (r2.y < c.rc2)) : (r2.y < c.rc2);
+        ir2.x = in0 ? ir2.x : 0.0f;
+        ir2.y = in1 ? ir2.y : 0.0f;
+    } else if (KEEPTEST) {
+        ir2.x = keep0 ? ir2.x : 0.0f;
+        ir2.y = keep1 ? ir2.y : 0.0f;
+    }
+    const float2 ir6 = __fmul2_rn(__fmul2_rn(ir2, ir2), ir2);
+    f = __fmul2_rn(__ffma2_rn(ir6, c2.c12, c2.nc6), __fmul2_rn(ir6, ir2));
+    if (PE) pe2 = __ffma2_rn(ir6, __ffma2_rn(ir6, c2.d12, c2.nd6), pe2);
+}
+
 // jnp.mod(x, box) of MD:72 (result has the divisor's sign; can return exactly `box` for tiny
 // negative x).  Fast exact paths for the ranges a step can produce, generic fmodf otherwise.
 __device__ __forceinline__ float wrap_box(float x, float box) {
