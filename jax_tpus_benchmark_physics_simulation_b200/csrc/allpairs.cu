@@ -63,7 +63,9 @@ struct ApArgs {
     float2*          part;        // [G*maxseg*BLOCK_I] partial forces
     // Newton's-third-law tile mode (IPT == 3): upper-triangular patches of Pt x Pt tiles of 64 x 64
     int              Pt, q, npr;  // patch edge in tiles, tiles per warp edge (Pt = 2q), patch rows
-    const int*       cta_pstart;  // [G+1] range of `patches` owned by each CTA
+    const int*       cta_pstart;  // (unused: patches are handed out dynamically)
+    int              npatch, npe; // number of patches; number of energy partials per parity
+    int*             sched;       // [2] patch counters (by step parity)
     const int2*      patches;     // (pa, pb) patch coordinates, pa <= pb
     float2*          rowpart;     // [npatch][Pt*64] partial force on the patch's row (i) side
     float2*          colpart;     // [npatch][Pt*64] partial force on the patch's column (j) side
@@ -235,8 +237,16 @@ __device__ __forceinline__ void ap3_phase_forces(const ApArgs& a, const float2* 
     const PairConsts2 pc2 = make_pair_consts2(pc);
     float2* rowacc = sacc + (size_t)w * 2 * q * T3_BLK;        // this warp's [q][64] row-side sums
     float2* colacc = rowacc + (size_t)q * T3_BLK;              //             [q][64] column-side sums
-    float pe_thread = 0.0f;
-    for (int pi = a.cta_pstart[c]; pi < a.cta_pstart[c + 1]; ++pi) {
+    // CTA c takes patch c, then draws further patches from a per-step counter: rows of the triangle
+    // differ in cost (diagonal patches, padding) and so do the SMs' shares of the L2; results and
+    // partial sums are indexed by patch, so nothing depends on which CTA ran it.
+    __shared__ int s_pi;
+    for (int it = 0;; ++it) {
+        if (tid == 0) s_pi = (it == 0) ? c : a.G + atomicAdd(&a.sched[par], 1);
+        __syncthreads();
+        const int pi = s_pi;
+        if (pi >= a.npatch) break;
+        float pe_thread = 0.0f;
         const int2 pp = a.patches[pi];
         const int pid = tri_base(pp.x, a.npr) + (pp.y - pp.x);
         for (int k = lane; k < q * T3_BLK; k += 32) colacc[k] = make_float2(0.0f, 0.0f);
@@ -288,11 +298,11 @@ __device__ __forceinline__ void ap3_phase_forces(const ApArgs& a, const float2* 
             __stcg(&rp[k], make_float2(ra0->x + ra1->x, ra0->y + ra1->y));
             __stcg(&cp[k], make_float2(ca0->x + ca1->x, ca0->y + ca1->y));
         }
+        if (PE) {                                    // per-patch energy partial (fixed reduction tree)
+            float t = block_sum<AP_THREADS>(pe_thread, sred);
+            if (tid == 0) __stcg(&a.pe_part[par * a.npe + pid], t);
+        }
         __syncthreads();
-    }
-    if (PE) {
-        float t = block_sum<AP_THREADS>(pe_thread, sred);
-        if (tid == 0) __stcg(&a.pe_part[par * a.G + c], t);
     }
 }
 
@@ -319,7 +329,7 @@ __device__ __forceinline__ void ap_phase_forces(const ApArgs& a, const float2* _
     }
     if (PE) {
         float t = block_sum<AP_THREADS>(pe_thread, sred);
-        if (tid == 0) __stcg(&a.pe_part[par * a.G + c], t);
+        if (tid == 0) __stcg(&a.pe_part[par * a.npe + c], t);
     }
 }
 
@@ -362,6 +372,7 @@ ap_persistent_kernel(const ApArgs a) {
         if (prof) pt[4] = clock64();
         // ---- [b] partial forces of R_cur ------------------------------------------------------
         if constexpr (V3) {
+            if (c == 0 && tid == 0) __stcg(&a.sched[par ^ 1], 0);   // the other parity's patch counter
             if (want_pe) ap3_phase_forces<CUTOFF, true >(a, Rcur, reinterpret_cast<float2*>(smem_buf), sred, par);
             else         ap3_phase_forces<CUTOFF, false>(a, Rcur, reinterpret_cast<float2*>(smem_buf), sred, par);
         } else {
@@ -508,7 +519,7 @@ ap_persistent_kernel(const ApArgs a) {
 
         // ---- energies of the post-step state (one warp, fixed order, double combine) ----------
         if (c == 0 && tid < 32 && want_pe) {
-            double pe2 = warp_sum_array(a.pe_part + par * a.G, a.G);
+            double pe2 = warp_sum_array(a.pe_part + par * a.npe, a.npe);
             double ke2 = want_e ? warp_sum_array(a.ke_part + par * a.G, a.G) : 0.0;
             if (tid == 0) {
                 if (want_e) {
@@ -591,7 +602,8 @@ gr_hist_kernel(const float2* __restrict__ Rh, int N, float box, float timg, int 
 // ----------------------------------------------------------------------------------------------
 struct AllPairs {
     int ipt = 1, G = 0, NJu = 0, nI = 0, maxseg = 0;
-    int Pt = 0, q = 0, npr = 0;                     // Newton's-third-law tile mode (ipt == 3)
+    int Pt = 0, q = 0, npr = 0, npatch = 0, npe = 0;   // Newton's-third-law tile mode (ipt == 3)
+    int* sched = nullptr;
     int*  d_cta_pstart = nullptr;
     int2* d_patches = nullptr;
     float2 *rowpart = nullptr, *colpart = nullptr;
@@ -660,6 +672,7 @@ int ap_create(ljmd_handle* h) {
         for (int pa = 0; pa < ap->npr; ++pa)
             for (int pb = pa; pb < ap->npr; ++pb) patches.push_back(make_int2(pa, pb));
         const long long npatch = (long long)patches.size();
+        ap->npatch = (int)npatch;
         ap->G = (int)std::min<long long>(slots, npatch);
         if (const char* e = getenv("LJMD_AP_GRID")) ap->G = std::max(1, std::min(atoi(e), ap->G));
         pstart.resize(ap->G + 1);
@@ -755,7 +768,9 @@ int ap_create(ljmd_handle* h) {
         LJ_CUDA(cudaMalloc(&ap->rowpart, sizeof(float2) * np * ps));
         LJ_CUDA(cudaMalloc(&ap->colpart, sizeof(float2) * np * ps));
     }
-    LJ_CUDA(cudaMalloc(&ap->pe_part, sizeof(float) * 2 * ap->G));
+    ap->npe = (ap->ipt == 3) ? (int)patches.size() : ap->G;
+    LJ_CUDA(cudaMalloc(&ap->pe_part, sizeof(float) * 2 * ap->npe));
+    LJ_CUDA(cudaMalloc(&ap->sched, sizeof(int) * 2));
     LJ_CUDA(cudaMalloc(&ap->ke_part, sizeof(float) * 2 * ap->G));
     LJ_CUDA(cudaMalloc(&ap->bar, sizeof(unsigned)));
     LJ_CUDA(cudaMalloc(&ap->err, sizeof(int)));
@@ -771,6 +786,7 @@ void ap_destroy(ljmd_handle* h) {
     cudaFree(ap->shared); cudaFree(ap->Vh); cudaFree(ap->Ftmp);
     cudaFree(ap->part); cudaFree(ap->pe_part); cudaFree(ap->ke_part);
     cudaFree(ap->d_cta_pstart); cudaFree(ap->d_patches); cudaFree(ap->rowpart); cudaFree(ap->colpart);
+    cudaFree(ap->sched);
     cudaFree(ap->bar); cudaFree(ap->err);
     delete ap;
     h->ap = nullptr;
@@ -797,7 +813,7 @@ int ap_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_out
     a.cta_start = ap->d_cta_start; a.cta_ib0 = ap->d_cta_ib0; a.iblk_ctas = ap->d_iblk;
     a.R_in = R_in; a.Rbuf0 = ap->Rbuf0; a.Rbuf1 = ap->Rbuf1; a.Vh = ap->Vh; a.Ftmp = ap->Ftmp;
     a.part = ap->part; a.pe_part = ap->pe_part; a.ke_part = ap->ke_part;
-    a.Pt = ap->Pt; a.q = ap->q; a.npr = ap->npr;
+    a.Pt = ap->Pt; a.q = ap->q; a.npr = ap->npr; a.npatch = ap->npatch; a.npe = ap->npe; a.sched = ap->sched;
     a.cta_pstart = ap->d_cta_pstart; a.patches = ap->d_patches; a.rowpart = ap->rowpart; a.colpart = ap->colpart;
     a.bar = ap->bar; a.err = ap->err; a.prof = ap->prof;
     a.rc = rc;
@@ -817,6 +833,7 @@ int ap_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_out
         a.xepoch0 = ap->xepoch;
         if (a.P > 1) { int rb = dist_barrier(h); if (rb) return rb; }   // the ranks enter the kernel together
         LJ_CUDA(cudaMemsetAsync(ap->bar, 0, sizeof(unsigned), st));
+        LJ_CUDA(cudaMemsetAsync(ap->sched, 0, sizeof(int) * 2, st));
         void* args[] = {(void*)&a};
         LJ_CUDA(cudaLaunchCooperativeKernel((void*)ap->kernel, dim3(ap->G), dim3(AP_THREADS), args, 0, st));
         h->launches++;
