@@ -138,6 +138,10 @@ int ljmd_create_dist(ljmd_t** out, const ljmd_params* p, const void* nccl_unique
 /* device time (ms) of the last ljmd_run's step loop, measured with CUDA events on the
  * handle's stream (blocks until that run has finished).                             */
 int ljmd_last_run_ms(ljmd_t* h, float* ms);
+/* all-pairs evaluation mode chosen at create: 1 / 2 = every ORDERED pair is evaluated (one / two
+ * i-particles per thread), 3 = Newton's-third-law tiles: every UNORDERED pair is evaluated once and
+ * applied to both particles (atomic-free; single GPU, N >= 2048).  0 on the cell-list path.       */
+int ljmd_allpairs_mode(ljmd_t* h, int32_t* mode);
 /* number of kernel launches issued by this handle since creation                    */
 int ljmd_launch_count(ljmd_t* h, int64_t* launches);
 /* FP32 issue-rate micro-benchmarks (FFMA / FFMA2 dependent chains): returns achieved

@@ -19,7 +19,7 @@ EXPORTS = (
     "ljmd_abi_version", "ljmd_last_error", "ljmd_create", "ljmd_destroy", "ljmd_energy",
     "ljmd_forces", "ljmd_run", "ljmd_gr_hist", "ljmd_cell_geometry", "ljmd_cell_assign",
     "ljmd_neighbor_count", "ljmd_last_rebuilds", "ljmd_get_unique_id", "ljmd_create_dist",
-    "ljmd_last_run_ms", "ljmd_launch_count", "ljmd_fp32_peak_probe",
+    "ljmd_last_run_ms", "ljmd_launch_count", "ljmd_fp32_peak_probe", "ljmd_allpairs_mode",
 )
 
 
@@ -77,6 +77,7 @@ def load() -> ctypes.CDLL:
     lib.ljmd_create_dist.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(LjmdParams), vp, i32, i32]
     lib.ljmd_last_run_ms.argtypes = [vp, ctypes.POINTER(f32)]
     lib.ljmd_launch_count.argtypes = [vp, ctypes.POINTER(i64)]
+    lib.ljmd_allpairs_mode.argtypes = [vp, ctypes.POINTER(i32)]
     lib.ljmd_fp32_peak_probe.argtypes = [i32, i32, ctypes.POINTER(f32)]
     for name in EXPORTS:
         fn = getattr(lib, name)

@@ -625,6 +625,8 @@ struct AllPairs {
     ApKernel kernel = nullptr;
 };
 
+int ap_mode(ljmd_handle* h) { return h->ap ? h->ap->ipt : 0; }
+
 int ap_create(ljmd_handle* h) {
     AllPairs* ap = new AllPairs();
     h->ap = ap;

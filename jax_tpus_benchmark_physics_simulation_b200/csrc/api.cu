@@ -212,6 +212,12 @@ int ljmd_last_run_ms(ljmd_t* h, float* ms) {
     return e ? e : cells_check_error(h);
 }
 
+int ljmd_allpairs_mode(ljmd_t* h, int32_t* mode) {
+    if (!h || !mode) { set_error("null argument"); return LJMD_E_INVALID; }
+    *mode = (h->path == LJMD_PATH_ALLPAIRS) ? ap_mode(h) : 0;
+    return 0;
+}
+
 int ljmd_launch_count(ljmd_t* h, int64_t* launches) {
     if (!h || !launches) { set_error("null argument"); return LJMD_E_INVALID; }
     *launches = h->launches;

@@ -88,6 +88,7 @@ void ap_destroy(ljmd_handle* h);
 int  ap_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_out, float2* V_out,
             float2* F_out, float* pe_out, const RunCtl& rc);
 int  ap_check_error(ljmd_handle* h);
+int  ap_mode(ljmd_handle* h);
 int  ap_gr_hist(ljmd_handle* h, const float2* R_hist, long long S, int nbins, const float* edges,
                 long long* counts);
 

@@ -309,6 +309,13 @@ class LJSimulation:
         _lib.check(self.lib.ljmd_last_run_ms(self._h, ctypes.byref(v)), "ljmd_last_run_ms")
         return v.value
 
+    def allpairs_mode(self) -> int:
+        """1 / 2: every ordered pair evaluated; 3: Newton's-third-law tiles (each unordered pair
+        once); 0: cell-list path."""
+        v = ctypes.c_int32()
+        _lib.check(self.lib.ljmd_allpairs_mode(self._h, ctypes.byref(v)), "ljmd_allpairs_mode")
+        return v.value
+
     def launch_count(self) -> int:
         v = ctypes.c_int64()
         _lib.check(self.lib.ljmd_launch_count(self._h, ctypes.byref(v)), "ljmd_launch_count")
