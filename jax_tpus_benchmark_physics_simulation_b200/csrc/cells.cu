@@ -847,6 +847,12 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
                 moved |= (ddx * ddx + ddy * ddy > a.half_skin2);
             }
         }
+        // the warps that pushed halo particles order those peer stores at system scope now (hidden behind
+        // the other warps' work) instead of every thread of the grid fencing at the end of the step
+        if (a.P > 1 && !fl.thermo && !fl.final) {
+            const bool pushed = live && (i < first_e || i >= last_s);
+            if (__any_sync(0xffffffffu, pushed)) __threadfence_system();
+        }
         // per-unit energy partials (fixed shuffle tree), summed in unit order after the barrier
         if (PE) {
             const float t = warp_sum(pe);
@@ -988,7 +994,6 @@ cells_persistent_kernel(const CellsArgs a) {
         // a particle left the skin/2 ball: ask for a rebuild before the next force evaluation.
         // The flag carries the step stamp, so it never needs clearing (no reset race).
         if (__syncthreads_or(moved) && tid == 0) __stcg(a.state + (a.P > 1 ? ST_LMOVED : ST_FLAG), (int)(s + 2));
-        if (a.P > 1) __threadfence_system();                 // halo pushes visible before the arrival word
         if (!final) ctx.pr ^= 1;
         CL_PROF(0);
         CL_BARRIER();
@@ -1298,6 +1303,11 @@ int cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_
             double mean = 0, mx = 0;
             for (int c = 0; c < cl->G; ++c) { mean += pv[c * 12 + k]; mx = std::max<double>(mx, (double)pv[c * 12 + k]); }
             fprintf(stderr, "[ljmd cells prof] %-16s mean %12.0f  max %12.0f clocks (launch total)\n", nm[k], mean / cl->G, mx);
+        }
+        if (getenv("LJMD_CELLS_PROF_CTAS")) {
+            fprintf(stderr, "[ljmd cells prof] force+integrate clocks by CTA (launch total, /1000):");
+            for (int c = 0; c < cl->G; ++c) fprintf(stderr, "%s%lld", (c % 16) ? " " : "\n  ", pv[c * 12] / 1000);
+            fprintf(stderr, "\n");
         }
     }
     return 0;
