@@ -333,12 +333,13 @@ def main():
         # persistent kernel: one launch = md_steps steps + the prologue force evaluation
         evals = md_steps + 1
         pairs = float(N) * float(N - 1) * evals / (world if sharded else 1)      # ORDERED pairs
-        n3l = sim.allpairs_mode() == 3
+        ap_mode = sim.allpairs_mode()
+        n3l = ap_mode == 3
         # executed work: the N3L kernel evaluates each unordered pair once (report that count
         # for roofline.achieved; the headline pair rate keeps the ordered-pair denominator)
         executed_flop = (FLOP_PER_UNORDERED_N3L * pairs / 2.0) if n3l else (FLOP_PER_PAIR_FORCE * pairs)
         achieved = executed_flop / (launch_ms * 1e-3) / 1e12
-        peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12      # whole GPU (the cluster kernel uses 16 of the 148 SMs)
         try:
             probe = {"ffma_tflops": fp32_peak_probe(local_rank, False),
                      "ffma2_tflops": fp32_peak_probe(local_rank, True)}
@@ -349,8 +350,10 @@ def main():
                     "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz={sm_max:.0f} from "
                                    f"MEASURED_PEAKS.json ({peaks_src}); CUDA-core FP32, no tensor cores",
                     "measured_fp32_probe": probe,
-                    "kernel": "ap_persistent_kernel", "mode": "newton3 tiles (each unordered pair once)" if n3l
-                              else "ordered pairs",
+                    "kernel": "ap_cluster_kernel" if ap_mode == 4 else "ap_persistent_kernel",
+                    "mode": "newton3 tiles (each unordered pair once)" if n3l
+                            else ("ordered pairs, one 16-CTA cluster, state in distributed shared memory"
+                                  if ap_mode == 4 else "ordered pairs"),
                     "flop_per_evaluation": FLOP_PER_UNORDERED_N3L if n3l else FLOP_PER_PAIR_FORCE,
                     "ordered_pairs_per_launch": pairs,
                     "ordered_pair_equivalent_tflops": FLOP_PER_PAIR_FORCE * pairs / (launch_ms * 1e-3) / 1e12,

@@ -140,7 +140,9 @@ int ljmd_create_dist(ljmd_t** out, const ljmd_params* p, const void* nccl_unique
 int ljmd_last_run_ms(ljmd_t* h, float* ms);
 /* all-pairs evaluation mode chosen at create: 1 / 2 = every ORDERED pair is evaluated (one / two
  * i-particles per thread), 3 = Newton's-third-law tiles: every UNORDERED pair is evaluated once and
- * applied to both particles (atomic-free; single GPU, N >= 2048).  0 on the cell-list path.       */
+ * applied to both particles (atomic-free; single GPU, N >= 2048), 4 = ordered pairs inside ONE
+ * thread-block cluster with the state resident in distributed shared memory (single GPU, N <= 640).
+ * 0 on the cell-list path.                                                                        */
 int ljmd_allpairs_mode(ljmd_t* h, int32_t* mode);
 /* number of kernel launches issued by this handle since creation                    */
 int ljmd_launch_count(ljmd_t* h, int64_t* launches);

@@ -21,8 +21,12 @@
 // and written once per step.
 #include "ljmd_device.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstdio>
+
+namespace cg = cooperative_groups;
 
 namespace ljmd {
 
@@ -538,6 +542,267 @@ ap_persistent_kernel(const ApArgs a) {
     }
 }
 
+// ---- small systems: ONE thread-block cluster, state resident in distributed shared memory --------
+// At N <= ~1000 (config 1 is N = 400) a step holds so little work that the grid kernel above spends
+// its time in two grid barriers and ~6 L2 round trips.  Here the whole system lives on chip:
+//   * every CTA of the cluster keeps ALL positions in shared memory (ping-pong, as (-x,-x,-y,-y) so one
+//     LDS.128 feeds the packed pair evaluation);
+//   * CTA k owns particles [k*n_i, (k+1)*n_i).  A group of S lanes (S <= 32, one warp or part of one)
+//     shares a PAIR of them: lane sl evaluates the pair against the j slice sl, an xor-butterfly of
+//     shuffles leaves the bit-identical total force in all S lanes, and every lane finishes the
+//     velocity-Verlet step of the pair redundantly with the velocities in REGISTERS for the whole call;
+//   * lane sl then stores the new positions straight into the next-position buffer of CTA sl, sl+S, ...
+//     of the cluster (st.shared::cluster: one warp instruction reaches up to 32 CTAs' worth of
+//     destinations; a single thread pushing to 16 CTAs in turn measured ~190 clocks per store), and
+//     ONE hardware cluster barrier (barrier.cluster arrive.release / wait.acquire) ends the step.
+// No global memory traffic between samples, no L2 round trip, no __syncthreads on the step path.
+constexpr int CLU_THREADS = 512;
+constexpr int CLU_MAXC    = 16;
+
+struct CluArgs {
+    PairConsts pc;
+    int   N, C, n_i, half, S, jl;       // half: particle pairs per CTA; S lanes per pair, slices of jl (odd) particles
+    float dt, r2min;                    // r2min: see clu_pair2_f
+    const float2* R_in;
+    float2 *Rbuf0, *Rbuf1, *Vh;
+    long long s_begin, s_end;
+    RunCtl rc;
+    float2 *R_out, *V_out, *F_out;
+    float*  pe_out;
+    long long* prof;                    // optional [C][4] phase clocks (debug: LJMD_AP_PROF=1)
+};
+
+// The force-only slice loop is PREDICATE-FREE.  Inside the kernel the seven predicate registers are held
+// by loop-invariant step flags; with the usual compare+select forms the compiler funnelled every compare
+// of the four unrolled pair evaluations through the one or two registers left (measured: IPC 0.5).
+//   * minimum image: d - m * copysign(box, d) with m = (|d| >= timg) as 1.0f / 0.0f (FSET.BF + FFMA, one
+//     rounding: bit-identical to min_image());
+//   * cutoff: ir2 *= (r2 < rc2) as 1.0f / 0.0f (FSET.BF + one packed FMUL2);
+//   * the i == j term: r2 is clamped from below (FMNMX) at r2min, chosen on the host so that the force
+//     scalar stays finite there; dx = dy = 0 then makes the term exactly 0, as the reference's
+//     diagonal mask does (MD:54-55).  Distinct particles closer than sqrt(r2min) ~ 0.003 sigma overflow
+//     fp32 in the reference itself.  The energy variant (rare steps) keeps the exact index test.
+struct SliceSum { float2 fx, fy, pe; };
+
+__device__ __forceinline__ float set_ge_f32(float a, float b) {       // 1.0f if a >= b else 0.0f, in a register
+    float m;
+    asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(m) : "f"(a), "f"(b));
+    return m;
+}
+__device__ __forceinline__ float set_lt_f32(float a, float b) {
+    float m;
+    asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(m) : "f"(a), "f"(b));
+    return m;
+}
+__device__ __forceinline__ float min_image_bf(float d, float box, float timg) {
+    return fmaf(-set_ge_f32(fabsf(d), timg), copysignf(box, d), d);
+}
+
+template <bool CUTOFF>
+__device__ __forceinline__ void clu_pair2_f(float2 xi2, float2 yi2, float4 q, float r2min, const PairConsts& c,
+                                            const PairConsts2& c2, float2& fx2, float2& fy2) {
+    float2 dx = __fadd2_rn(xi2, make_float2(q.x, q.y));
+    float2 dy = __fadd2_rn(yi2, make_float2(q.z, q.w));
+    dx.x = min_image_bf(dx.x, c.box, c.timg); dx.y = min_image_bf(dx.y, c.box, c.timg);
+    dy.x = min_image_bf(dy.x, c.box, c.timg); dy.y = min_image_bf(dy.y, c.box, c.timg);
+    float2 r2 = __ffma2_rn(__fmul2_rn(dx, dx), c2.one, __fmul2_rn(dy, dy));         // unfused sum
+    r2.x = fmaxf(r2.x, r2min); r2.y = fmaxf(r2.y, r2min);
+    float2 ir2 = make_float2(rcp_approx(r2.x), rcp_approx(r2.y));
+    if (CUTOFF) {
+        const float2 m = make_float2(set_lt_f32(r2.x, c.rc2), set_lt_f32(r2.y, c.rc2));
+        ir2 = __fmul2_rn(ir2, m);
+    }
+    const float2 ir6 = __fmul2_rn(__fmul2_rn(ir2, ir2), ir2);
+    const float2 f = __fmul2_rn(__ffma2_rn(ir6, c2.c12, c2.nc6), __fmul2_rn(ir6, ir2));
+    fx2 = __ffma2_rn(f, dx, fx2);
+    fy2 = __ffma2_rn(f, dy, fy2);
+}
+
+template <bool CUTOFF>
+__device__ __forceinline__ SliceSum clu_slice_f(const float4* cur, int j0, int j1, float2 xi2, float2 yi2,
+                                                float r2min, const PairConsts& pc) {
+    const PairConsts2 pc2 = make_pair_consts2(pc);
+    SliceSum r;
+    r.fx = make_float2(0.0f, 0.0f); r.fy = r.fx; r.pe = r.fx;
+#pragma unroll 4
+    for (int j = j0; j < j1; ++j) clu_pair2_f<CUTOFF>(xi2, yi2, cur[j], r2min, pc, pc2, r.fx, r.fy);
+    return r;
+}
+
+template <bool CUTOFF>
+__device__ __noinline__ SliceSum clu_slice_pe(const float4* cur, int j0, int j1, int i0, int i1, float2 xi2,
+                                              float2 yi2, PairConsts pc) {
+    const PairConsts2 pc2 = make_pair_consts2(pc);
+    SliceSum r;
+    r.fx = make_float2(0.0f, 0.0f); r.fy = r.fx; r.pe = r.fx;
+#pragma unroll 2
+    for (int j = j0; j < j1; ++j) {
+        const float4 q = cur[j];
+        pair2_accum<CUTOFF, true, true>(xi2, yi2, make_float2(q.x, q.y), make_float2(q.z, q.w), j != i0, j != i1,
+                                        pc, pc2, r.fx, r.fy, r.pe);
+    }
+    return r;
+}
+
+template <bool CUTOFF>
+__global__ void __launch_bounds__(CLU_THREADS, 1)
+ap_cluster_kernel(const CluArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int k = (int)cluster.block_rank(), tid = threadIdx.x;
+    extern __shared__ __align__(16) unsigned char clu_smem[];
+    float4* spos = reinterpret_cast<float4*>(clu_smem);                // [2][N]
+    float*  sE   = reinterpret_cast<float*>(spos + 2 * (size_t)a.N);   // [2 parity][pe, ke][CLU_MAXC] (CTA 0 sums)
+    float*  sK   = sE + 4 * CLU_MAXC;                                  // [CLU_MAXC] thermostat kinetic partials
+    float*  sred = sK + CLU_MAXC;                                      // [CLU_THREADS / 32]
+    __shared__ float s_lambda;
+    const RunCtl rc = a.rc;
+    const PairConsts pc = a.pc;
+    const int i_lo = min(a.N, k * a.n_i), i_hi = min(a.N, i_lo + a.n_i);
+    const int sl = tid & (a.S - 1), p = tid / a.S;                     // j slice, pair of particles
+    const int i0 = i_lo + p, i1 = i_lo + a.half + p;
+    const bool has0 = (p < a.half) && i0 < i_hi, has1 = (p < a.half) && i1 < i_hi;
+    const int j0 = min(a.N, sl * a.jl), j1 = min(a.N, j0 + a.jl);
+    const bool lead = (sl == 0);                                       // writes the pair's global outputs
+    float2 v0 = make_float2(0.0f, 0.0f), v1 = v0;                      // replicated in the S lanes of the pair
+    if (rc.nsteps > 0) {
+        if (has0) v0 = a.Vh[i0];
+        if (has1) v1 = a.Vh[i1];
+    }
+    {
+        const float2* Rsrc = (a.s_begin < 0) ? a.R_in : ((a.s_begin & 1) ? a.Rbuf1 : a.Rbuf0);
+        for (int j = tid; j < a.N; j += CLU_THREADS) {
+            const float2 r = Rsrc[j];
+            spos[j] = make_float4(-r.x, -r.x, -r.y, -r.y);
+        }
+    }
+    int b = 0;
+    long long pt[4] = {0, 0, 0, 0}, tl = 0;
+    const bool prof = a.prof != nullptr && tid == 0;
+    cluster.sync();                       // every CTA of the cluster is resident before remote stores start
+
+    for (long long s = a.s_begin; s < a.s_end; ++s) {
+        const int  par     = (int)((s + 1) & 1);
+        const bool kick1   = (s >= 0);
+        const bool final   = (s == rc.nsteps - 1);
+        const bool want_e  = kick1 && rc.energy_every > 0 && (s % rc.energy_every == 0);
+        const bool want_pe = want_e || (rc.nsteps == 0 && a.pe_out != nullptr);
+        const bool thermo  = kick1 && rc.thermo_every > 0 && rc.thermo_kT > 0.0f &&
+                             ((s + 1) % rc.thermo_every == 0);
+        const bool sample  = kick1 && rc.sample_every > 0 && (s % rc.sample_every == 0) &&
+                             (s / rc.sample_every < rc.S);
+        const float4* cur = spos + (size_t)b * a.N;
+        float4*       nxt = spos + (size_t)(b ^ 1) * a.N;
+        if (prof) tl = clock64();
+
+        // ---- forces on the pair from this lane's j slice, then the butterfly over the S lanes -------
+        float4 c0 = make_float4(-SENT_I, -SENT_I, -SENT_I, -SENT_I), c1 = c0;
+        if (has0) c0 = cur[i0];
+        if (has1) c1 = cur[i1];
+        const float2 xi2 = make_float2(-c0.x, -c1.x), yi2 = make_float2(-c0.z, -c1.z);
+        const SliceSum ss = want_pe ? clu_slice_pe<CUTOFF>(cur, j0, j1, i0, i1, xi2, yi2, pc)
+                                    : clu_slice_f<CUTOFF>(cur, j0, j1, xi2, yi2, a.r2min, pc);
+        float2 tfx = ss.fx, tfy = ss.fy;
+        const float2 tpe = ss.pe;
+        for (int o = a.S >> 1; o > 0; o >>= 1) {          // commutative adds: all lanes end bit-identical
+            tfx.x += __shfl_xor_sync(0xffffffffu, tfx.x, o);
+            tfx.y += __shfl_xor_sync(0xffffffffu, tfx.y, o);
+            tfy.x += __shfl_xor_sync(0xffffffffu, tfy.x, o);
+            tfy.y += __shfl_xor_sync(0xffffffffu, tfy.y, o);
+        }
+        if (want_pe) {                     // fixed tree: per-CTA potential energy -> CTA 0
+            const float t = block_sum<CLU_THREADS>((has0 ? tpe.x : 0.0f) + (has1 ? tpe.y : 0.0f), sred);
+            if (tid == 0) *cluster.map_shared_rank(&sE[(par * 2 + 0) * CLU_MAXC + k], 0) = t;
+        }
+        if (prof) { const long long t = clock64(); pt[0] += t - tl; tl = t; }
+
+        // ---- finish the velocity-Verlet step of the pair (every lane of the group, redundantly) -------
+        const float2 r0 = make_float2(-c0.x, -c0.z), r1 = make_float2(-c1.x, -c1.z);
+        if (kick1) {                                                                              // MD:74
+            v0.x = kick(v0.x, tfx.x, a.dt); v0.y = kick(v0.y, tfy.x, a.dt);
+            v1.x = kick(v1.x, tfx.y, a.dt); v1.y = kick(v1.y, tfy.y, a.dt);
+        }
+        if (sample && lead) {                                                                     // MD:93-100
+            float2* row = rc.traj + (size_t)(s / rc.sample_every) * a.N;
+            if (has0) row[i0] = r0;
+            if (has1) row[i1] = r1;
+        }
+        if (want_e || thermo) {
+            float ke_thread = 0.0f;
+            if (lead && has0) ke_thread += v0.x * v0.x + v0.y * v0.y;
+            if (lead && has1) ke_thread += v1.x * v1.x + v1.y * v1.y;
+            const float t = block_sum<CLU_THREADS>(ke_thread, sred);
+            if (tid == 0) {
+                if (want_e) *cluster.map_shared_rank(&sE[(par * 2 + 1) * CLU_MAXC + k], 0) = t;
+                if (thermo)
+                    for (int q = 0; q < a.C; ++q) *cluster.map_shared_rank(&sK[k], q) = t;
+            }
+        }
+        if (thermo) {
+            // velocity rescale: V *= sqrt(kT_target / (KE/N)); every CTA sums the same C partials
+            cluster.sync();
+            if (tid == 0) {
+                double ke2 = 0.0;
+                for (int q = 0; q < a.C; ++q) ke2 += (double)sK[q];
+                const float ke = (float)(0.5 * ke2);
+                s_lambda = sqrtf(rc.thermo_kT / (ke / (float)a.N));
+            }
+            __syncthreads();
+            const float lam = s_lambda;
+            v0.x *= lam; v0.y *= lam; v1.x *= lam; v1.y *= lam;
+        }
+        if (final) {
+            if (lead && has0) {
+                if (a.R_out) a.R_out[i0] = r0;
+                if (a.V_out) a.V_out[i0] = v0;
+                if (a.F_out) a.F_out[i0] = make_float2(tfx.x, tfy.x);
+            }
+            if (lead && has1) {
+                if (a.R_out) a.R_out[i1] = r1;
+                if (a.V_out) a.V_out[i1] = v1;
+                if (a.F_out) a.F_out[i1] = make_float2(tfx.y, tfy.y);
+            }
+        } else {
+            v0.x = kick(v0.x, tfx.x, a.dt); v0.y = kick(v0.y, tfy.x, a.dt);                       // MD:70
+            v1.x = kick(v1.x, tfx.y, a.dt); v1.y = kick(v1.y, tfy.y, a.dt);
+            const float2 n0 = make_float2(drift(r0.x, v0.x, a.dt, pc.box), drift(r0.y, v0.y, a.dt, pc.box));   // MD:71-72
+            const float2 n1 = make_float2(drift(r1.x, v1.x, a.dt, pc.box), drift(r1.y, v1.y, a.dt, pc.box));
+            const float4 q0 = make_float4(-n0.x, -n0.x, -n0.y, -n0.y), q1 = make_float4(-n1.x, -n1.x, -n1.y, -n1.y);
+            for (int q = sl; q < a.C; q += a.S) {
+                if (has0) *cluster.map_shared_rank(&nxt[i0], q) = q0;
+                if (has1) *cluster.map_shared_rank(&nxt[i1], q) = q1;
+            }
+            if (s == a.s_end - 1 && lead) {      // the next launch of a long call resumes from global memory
+                float2* Rg = ((s + 1) & 1) ? a.Rbuf1 : a.Rbuf0;
+                if (has0) { Rg[i0] = n0; a.Vh[i0] = v0; }
+                if (has1) { Rg[i1] = n1; a.Vh[i1] = v1; }
+            }
+        }
+        if (prof) { const long long t = clock64(); pt[1] += t - tl; tl = t; }
+        cluster.sync();                          // all next positions have landed in every CTA
+        if (prof) { const long long t = clock64(); pt[2] += t - tl; tl = t; }
+        b ^= 1;
+
+        if (k == 0 && tid == 0 && want_pe) {     // energies of the post-step state (fixed order, double)
+            double pe2 = 0.0, ke2 = 0.0;
+            for (int q = 0; q < a.C; ++q) pe2 += (double)sE[(par * 2 + 0) * CLU_MAXC + q];
+            if (want_e) {
+                for (int q = 0; q < a.C; ++q) ke2 += (double)sE[(par * 2 + 1) * CLU_MAXC + q];
+                float* o = rc.ke_pe + 2 * (s / rc.energy_every);
+                o[0] = (float)(0.5 * ke2);
+                o[1] = (float)(0.5 * pe2);       // MD:61  0.5 * sum over ordered pairs
+            } else {
+                a.pe_out[0] = (float)(0.5 * pe2);
+            }
+        }
+    }
+    if (prof) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a.prof[k * 4 + q] = pt[q];
+    }
+}
+
+using CluKernel = void (*)(const CluArgs);
+
 using ApKernel = void (*)(const ApArgs);
 
 ApKernel pick_kernel(int ipt, bool cutoff) {
@@ -623,9 +888,50 @@ struct AllPairs {
     int* err = nullptr;
     long long* prof = nullptr;
     ApKernel kernel = nullptr;
+    // single-cluster kernel for small systems (nullptr: not used)
+    CluKernel clu_kernel = nullptr;
+    int cluC = 0, clu_n_i = 0, clu_half = 0, clu_S = 0, clu_jl = 0;
+    size_t clu_smem = 0;
 };
 
-int ap_mode(ljmd_handle* h) { return h->ap ? h->ap->ipt : 0; }
+int ap_mode(ljmd_handle* h) { return h->ap ? (h->ap->clu_kernel ? 4 : h->ap->ipt) : 0; }
+
+// Can the whole system run inside one thread-block cluster?  (16 CTAs needs the non-portable opt-in.)
+static int clu_setup(ljmd_handle* h, AllPairs* ap) {
+    const long long N = h->p.N;
+    // measured crossover with the grid kernel (which can use all 148 SMs): N = 400: 3.7 vs 6.9 us/step,
+    // N = 1024: 9.0 vs 6.6 us/step
+    long long nmax = 640;
+    if (const char* e = getenv("LJMD_AP_CLUSTER_NMAX")) nmax = atoll(e);
+    if (std::max(1, h->nranks) != 1 || N > nmax || N > 4096) return 0;
+    CluKernel kern = h->pc.cutoff != 0 ? ap_cluster_kernel<true> : ap_cluster_kernel<false>;
+    const size_t smem = 32 * (size_t)N + sizeof(float) * (5 * CLU_MAXC + CLU_THREADS / 32);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int want = CLU_MAXC;
+    if (const char* e = getenv("LJMD_AP_CLUSTER_SIZE")) want = std::max(1, std::min(CLU_MAXC, atoi(e)));
+    for (int C = want; C >= 1; C >>= 1) {
+        if (C > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(C); cfg.blockDim = dim3(CLU_THREADS); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); continue; }
+        ap->clu_kernel = kern; ap->cluC = C; ap->clu_smem = smem;
+        ap->clu_n_i = (int)((N + C - 1) / C);
+        ap->clu_half = (ap->clu_n_i + 1) / 2;
+        if (ap->clu_half > CLU_THREADS) { ap->clu_kernel = nullptr; return 0; }
+        int S = 32;                                        // lanes per particle pair (one warp at most)
+        while (S > 1 && ap->clu_half * S > CLU_THREADS) S >>= 1;
+        while (S > 1 && (long long)S > N) S >>= 1;
+        ap->clu_S = S;
+        ap->clu_jl = (int)((N + S - 1) / S) | 1;           // odd slice length: conflict-free LDS.128 across lanes
+        return 0;
+    }
+    return 0;
+}
 
 int ap_create(ljmd_handle* h) {
     AllPairs* ap = new AllPairs();
@@ -643,6 +949,7 @@ int ap_create(ljmd_handle* h) {
     ap->nI  = (ap->Nloc + BI - 1) / BI;             // i-blocks of THIS rank's slab
     ap->NJu = (int)((N + J_UNIT - 1) / J_UNIT);
     ap->kernel = pick_kernel(ap->ipt, h->pc.cutoff != 0);
+    if (!getenv("LJMD_AP_IPT")) clu_setup(h, ap);      // (forcing a grid-kernel variant disables the cluster path)
 
     int per_sm = 0;
     LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ap->kernel, AP_THREADS, 0));
@@ -777,7 +1084,7 @@ int ap_create(ljmd_handle* h) {
     LJ_CUDA(cudaMalloc(&ap->bar, sizeof(unsigned)));
     LJ_CUDA(cudaMalloc(&ap->err, sizeof(int)));
     LJ_CUDA(cudaMemset(ap->err, 0, sizeof(int)));
-    if (getenv("LJMD_AP_PROF")) LJ_CUDA(cudaMalloc(&ap->prof, sizeof(long long) * 4 * ap->G));
+    if (getenv("LJMD_AP_PROF")) LJ_CUDA(cudaMalloc(&ap->prof, sizeof(long long) * 4 * std::max(ap->G, CLU_MAXC)));
     return 0;
 }
 
@@ -829,6 +1136,43 @@ int ap_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_out
     if (h->timed) LJ_CUDA(cudaEventRecord(h->ev0, st));
     long long s = -1;
     const long long s_last = rc.nsteps;     // exclusive
+    if (ap->clu_kernel) {
+        CluArgs c{};
+        c.pc = h->pc; c.N = (int)N; c.C = ap->cluC; c.n_i = ap->clu_n_i; c.half = ap->clu_half;
+        c.S = ap->clu_S; c.jl = ap->clu_jl; c.dt = h->p.dt;
+        c.r2min = 2.0f * powf(fabsf(h->pc.c12) / 3.0e38f, 1.0f / 7.0f);      // c12 / r2min^7 stays finite
+        c.R_in = R_in; c.Rbuf0 = ap->Rbuf0; c.Rbuf1 = ap->Rbuf1; c.Vh = ap->Vh;
+        c.rc = rc; c.R_out = R_out; c.V_out = V_out; c.F_out = F_out; c.pe_out = pe_out;
+        c.prof = ap->prof;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ap->cluC); cfg.blockDim = dim3(CLU_THREADS); cfg.dynamicSmemBytes = ap->clu_smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = ap->cluC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        while (s < s_last) {
+            const long long e = std::min(s_last, s + chunk);
+            c.s_begin = s; c.s_end = e;
+            LJ_CUDA(cudaLaunchKernelEx(&cfg, ap->clu_kernel, c));
+            h->launches++;
+            s = e;
+        }
+        if (h->timed) LJ_CUDA(cudaEventRecord(h->ev1, st));
+        if (ap->prof) {
+            LJ_CUDA(cudaStreamSynchronize(st));
+            std::vector<long long> pv(4 * ap->cluC);
+            LJ_CUDA(cudaMemcpy(pv.data(), ap->prof, sizeof(long long) * pv.size(), cudaMemcpyDeviceToHost));
+            const double nst = (double)std::max<long long>(1, c.s_end - c.s_begin);
+            const char* nm[3] = {"forces", "integrate+push", "cluster sync"};
+            for (int q = 0; q < 3; ++q) {
+                double mean = 0, mx = 0;
+                for (int j = 0; j < ap->cluC; ++j) { mean += pv[j * 4 + q]; mx = std::max<double>(mx, (double)pv[j * 4 + q]); }
+                fprintf(stderr, "[ljmd prof] %-12s mean %8.0f  max %8.0f clocks/step (cluster of %d)\n", nm[q],
+                        mean / ap->cluC / nst, mx / nst, ap->cluC);
+            }
+        }
+        return 0;
+    }
     while (s < s_last) {
         const long long e = std::min(s_last, s + chunk);
         a.s_begin = s; a.s_end = e;

@@ -311,7 +311,7 @@ class LJSimulation:
 
     def allpairs_mode(self) -> int:
         """1 / 2: every ordered pair evaluated; 3: Newton's-third-law tiles (each unordered pair
-        once); 0: cell-list path."""
+        once); 4: ordered pairs in one thread-block cluster (small N); 0: cell-list path."""
         v = ctypes.c_int32()
         _lib.check(self.lib.ljmd_allpairs_mode(self._h, ctypes.byref(v)), "ljmd_allpairs_mode")
         return v.value

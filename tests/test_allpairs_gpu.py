@@ -108,7 +108,7 @@ def test_half_box_tie_follows_round_half_even(oracle):
     assert np.abs(F - Fc).max() <= 1e-6 * max(1e-30, np.abs(Fc).max()) + 1e-12
 
 
-@pytest.mark.parametrize("N,rc", [(400, None), (400, 2.5), (4096, 2.5)])
+@pytest.mark.parametrize("N,rc", [(400, None), (400, 2.5), (1024, 2.5), (4096, 2.5)])
 def test_one_step_vs_oracle(oracle, N, rc):
     """SURVEY §8c KAT (5): one verlet_step vs the restatement; total energy within 1e-6."""
     dt = 0.005
@@ -175,6 +175,47 @@ def test_run_is_deterministic_and_composable():
     Rd0 = Rd.clone()
     sim.run((Rd, V), 5)
     assert torch.equal(Rd, Rd0)
+
+
+@pytest.mark.parametrize("N", [400, 1024, 4096])
+def test_kernel_variants_and_launch_chunking(N, monkeypatch):
+    """N = 400 runs in one thread-block cluster (mode 4), N = 1024 in the ordered grid kernel (mode 1),
+    N = 4096 in the Newton's-third-law tiles (mode 3).  A call split into several launches (state
+    handed over through global memory) gives the same bits as one launch, with samples and energies."""
+    R, V, box = lattice_jitter(N, seed=3)
+    sim = _sim(N, rc=2.5, dt=0.005)
+    assert sim.allpairs_mode() == {400: 4, 1024: 1, 4096: 3}[N]
+    (Ra, Va), ta = sim.run((R, V), 45, sample_every=10, energy_every=5)
+    ea = sim.last_energies.numpy().copy()
+    monkeypatch.setenv("LJMD_AP_CHUNK", "7")
+    (Rb, Vb), tb = sim.run((R, V), 45, sample_every=10, energy_every=5)
+    eb = sim.last_energies.numpy().copy()
+    monkeypatch.delenv("LJMD_AP_CHUNK")
+    assert np.array_equal(Ra.numpy(), Rb.numpy()) and np.array_equal(Va.numpy(), Vb.numpy())
+    assert np.array_equal(ta.numpy(), tb.numpy()) and np.array_equal(ea, eb)
+
+
+def test_cluster_kernel_matches_grid_kernel(monkeypatch):
+    """The single-cluster kernel (predicate-free pair loop, slices summed by a shuffle butterfly) and the
+    grid kernel evaluate the same ordered pairs: forces to rounding, 100-step trajectory before chaos."""
+    N = 400
+    R, V, box = lattice_jitter(N, seed=4)
+    clu = _sim(N, rc=None, dt=0.001)
+    monkeypatch.setenv("LJMD_AP_CLUSTER_NMAX", "0")
+    grid = _sim(N, rc=None, dt=0.001)
+    monkeypatch.delenv("LJMD_AP_CLUSTER_NMAX")
+    assert clu.allpairs_mode() == 4 and grid.allpairs_mode() == 1
+    Fc, pc = clu.force_and_energy(R)
+    Fg, pg = grid.force_and_energy(R)
+    assert np.abs(Fc.numpy() - Fg.numpy()).max() <= 2e-6 * np.abs(Fg.numpy()).max()
+    assert abs(float(pc) - float(pg)) <= 1e-6 * abs(float(pg))
+    (Rc, Vc), _ = clu.run((R, V), 100, energy_every=10)
+    ec = clu.last_energies.numpy().copy()
+    (Rg, Vg), _ = grid.run((R, V), 100, energy_every=10)
+    eg = grid.last_energies.numpy()
+    d = np.abs(Rc.numpy() - Rg.numpy()); d = np.minimum(d, float(box) - d)
+    assert d.max() <= 1e-4
+    assert np.abs(ec.sum(1) - eg.sum(1)).max() <= 2e-6 * np.abs(eg.sum(1)).max()
 
 
 def test_momentum_and_energy_conservation(oracle):
