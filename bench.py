@@ -34,6 +34,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# measured DRAM bytes per force evaluation (ncu --set full captures under profiles/)
+AP_TRAFFIC = {
+    "ap4096": (256512.0 / 1001.0, "profiles/r1_ap4096_n3l_final.ncu-rep: 256.5 KB per 1001-evaluation launch"),
+    "ap65536": (127447552.0 / 4.0, "profiles/r1_ap65536_n3l_v4.ncu-rep: 127.4 MB per 4-evaluation launch "
+                                   "(partial force vectors)"),
+}
+
 WORKLOADS = {
     "ap400":    dict(N=400, rc=None, dt=1e-3, path="allpairs", md_steps=2000,
                      desc="default 2D LJ run of the reference script (N=400, no cutoff, dt=1e-3)"),
@@ -358,6 +365,12 @@ def main():
                     "ordered_pairs_per_launch": pairs,
                     "ordered_pair_equivalent_tflops": FLOP_PER_PAIR_FORCE * pairs / (launch_ms * 1e-3) / 1e12,
                     "launch_ms": launch_ms}
+        if n3l and world == 1 and wl_name in AP_TRAFFIC:
+            # dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture, per force
+            # evaluation, scaled to this launch: the state and the partial vectors are L2 resident
+            per_eval, src = AP_TRAFFIC[wl_name]
+            roofline["traffic"] = per_eval * evals
+            roofline["traffic_source"] = src
     else:
         bytes_ = BYTES_PER_PARTICLE_STEP * N * md_steps
         achieved = bytes_ / (launch_ms * 1e-3) / 1e9
