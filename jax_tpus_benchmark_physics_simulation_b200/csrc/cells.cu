@@ -318,14 +318,24 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
         for (int q = tid; q < r; q += CL_THREADS) s += a.row_tot[q];
         int carry;
         (void)block_exscan(s, sscan, &carry);
-        for (int bb = 0; bb < a.nbx; bb += CL_THREADS) {
-            const int b = bb + tid;
-            int v = 0;
-            if (b < a.nbx) { v = __ldcg(&a.cell_count[r * a.nbx + b]); a.cell_count[r * a.nbx + b] = 0; }
-            int tot;
-            const int ex = block_exscan(v, sscan, &tot);
-            if (b < a.nbx) a.cell_start[r * a.nbx + b] = carry + ex;
-            carry += tot;
+        // eight 512-bin pieces of the row are loaded before the first scan (one memory latency per 4096
+        // bins instead of one per piece)
+        for (int bb0 = 0; bb0 < a.nbx; bb0 += 8 * CL_THREADS) {
+            int v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int b = bb0 + u * CL_THREADS + tid;
+                v[u] = (b < a.nbx) ? __ldcg(&a.cell_count[r * a.nbx + b]) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (bb0 + u * CL_THREADS >= a.nbx) break;              // block-uniform
+                const int b = bb0 + u * CL_THREADS + tid;
+                int tot;
+                const int ex = block_exscan(v[u], sscan, &tot);
+                if (b < a.nbx) { a.cell_start[r * a.nbx + b] = carry + ex; a.cell_count[r * a.nbx + b] = 0; }
+                carry += tot;
+            }
         }
         if (r == a.nlr - 1 && tid == 0) {
             a.cell_start[a.ncells] = carry;
