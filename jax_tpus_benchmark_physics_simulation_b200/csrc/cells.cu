@@ -47,6 +47,7 @@ namespace ljmd {
 
 namespace {
 
+constexpr int CL_B5 = 3;          // slots per thread per trip of the rebuild gather (B5)
 constexpr int CL_THREADS   = 512;
 constexpr int CL_K         = 4;     // bins per (rc + skin)
 constexpr int CL_E         = 8;     // list entries per particle (3 when every range fits 32 slots)
@@ -352,17 +353,22 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
     }
     // B4: scatter (source slot, original index, cell) into the cell's slot range, arrival order
     for (int k0 = gtid; k0 < nheld; k0 += 4 * gsz) {
+        int c[4], rk[4], og[4], cs0[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                       // stage 1: four independent streams
+            const int k = k0 + u * gsz;
+            c[u] = -1; rk[u] = 0; og[u] = 0;
+            if (k < nheld) { c[u] = a.key[k]; rk[u] = a.rank[k]; og[u] = orig_old[k]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cs0[u] = (c[u] >= 0) ? a.cell_start[c[u]] : 0;   // stage 2: four gathers
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int k = k0 + u * gsz;
-            if (k < nheld) {
-                const int c = a.key[k];
-                if (c >= 0) {
-                    const int d = min(a.cell_start[c] + a.rank[k], a.Nalloc - 1);
-                    a.tmpk[d] = k;
-                    a.tmpo[d] = orig_old[k];
-                    a.tmpc[d] = c;
-                }
+            if (c[u] >= 0) {
+                const int d = min(cs0[u] + rk[u], a.Nalloc - 1);
+                a.tmpk[d] = k0 + u * gsz;
+                a.tmpo[d] = og[u];
+                a.tmpc[d] = c[u];
             }
         }
     }
@@ -378,24 +384,52 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
         const float2* Vo = a.V[ctx.pv];
         float2* Vn = a.V[ctx.pv ^ 1];
         int* on = a.orig[ctx.pv ^ 1];
-        for (int d = own_s + gtid; d < own_e; d += gsz) {
-            const int c = a.tmpc[d];
-            const int b = a.cell_start[c], n = a.cell_start[c + 1] - b, p = d - b;
-            int msel = p;
-            if (n > 1 && n <= CL_ORDER_MAX) {
-                for (int m = 0; m < n; ++m) {
-                    const int om = a.tmpo[b + m];
-                    int rk = 0;
-                    for (int q = 0; q < n; ++q) rk += (a.tmpo[b + q] < om);
-                    if (rk == p) { msel = m; break; }
+        // CL_B5 slots per thread per trip: the chain slot -> cell -> cell range -> member -> state is four
+        // dependent loads long; independent chains divide the exposed latency (1 -> 2 chains: -27 %)
+        for (int d0 = own_s + gtid; d0 < own_e; d0 += CL_B5 * gsz) {
+            int dd[CL_B5], c[CL_B5], b[CL_B5], n[CL_B5], msel[CL_B5], ksel[CL_B5], osel[CL_B5];
+            bool ok[CL_B5];
+            float2 r[CL_B5], v[CL_B5];
+#pragma unroll
+            for (int u = 0; u < CL_B5; ++u) {
+                dd[u] = d0 + u * gsz;
+                ok[u] = dd[u] < own_e;
+                c[u] = ok[u] ? a.tmpc[dd[u]] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < CL_B5; ++u) {
+                b[u] = a.cell_start[c[u]];
+                n[u] = a.cell_start[c[u] + 1] - b[u];
+            }
+#pragma unroll
+            for (int u = 0; u < CL_B5; ++u) {
+                const int p = dd[u] - b[u];
+                msel[u] = p;
+                if (ok[u] && n[u] > 1 && n[u] <= CL_ORDER_MAX) {
+                    for (int m = 0; m < n[u]; ++m) {
+                        const int om = a.tmpo[b[u] + m];
+                        int rk = 0;
+                        for (int q = 0; q < n[u]; ++q) rk += (a.tmpo[b[u] + q] < om);
+                        if (rk == p) { msel[u] = m; break; }
+                    }
                 }
             }
-            const int ksel = a.tmpk[b + msel];
-            const float2 r = Rc[ksel];
-            Rn[d] = r;
-            a.Rb[d] = r;
-            Vn[d] = Vo[ksel];
-            on[d] = a.tmpo[b + msel];
+#pragma unroll
+            for (int u = 0; u < CL_B5; ++u) {
+                ksel[u] = ok[u] ? a.tmpk[b[u] + msel[u]] : 0;
+                osel[u] = ok[u] ? a.tmpo[b[u] + msel[u]] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < CL_B5; ++u) { r[u] = Rc[ksel[u]]; v[u] = Vo[ksel[u]]; }
+#pragma unroll
+            for (int u = 0; u < CL_B5; ++u) {
+                if (ok[u]) {
+                    Rn[dd[u]] = r[u];
+                    a.Rb[dd[u]] = r[u];
+                    Vn[dd[u]] = v[u];
+                    on[dd[u]] = osel[u];
+                }
+            }
         }
     }
     ctx.pr ^= 1;
@@ -451,12 +485,23 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
         const int* __restrict__ cs = a.cell_start;
         const PairConsts pc = a.pc;
         const int lane = tid & 31;
+        // (position, cell) of the NEXT unit's slot are requested a whole unit ahead
+        float2 rnext = make_float2(0.0f, 0.0f);
+        int cnext = 0;
+        {
+            const int i = (ctx.own_s & ~31) + (gtid & ~31) + lane;
+            if (i >= ctx.own_s && i < ctx.own_e) { rnext = R[i]; cnext = a.tmpc[i]; }
+        }
         for (int i0 = (ctx.own_s & ~31) + (gtid & ~31); i0 < ctx.own_e; i0 += gsz) {
             const int i = i0 + lane;
             const bool live = (i >= ctx.own_s) & (i < ctx.own_e);
-            float2 ri = make_float2(0.0f, 0.0f);
-            int c = 0;
-            if (live) { ri = R[i]; c = a.tmpc[i]; }
+            const float2 ri = rnext;
+            const int c = cnext;
+            {
+                const int in = i + gsz;
+                rnext = make_float2(0.0f, 0.0f); cnext = 0;
+                if (in >= ctx.own_s && in < ctx.own_e) { rnext = R[in]; cnext = a.tmpc[in]; }
+            }
             const int r = c / a.nbx, b = c - r * a.nbx;           // local row, bin
             const bool edge = edge_cell(a, r, b);
             // warp plan
@@ -465,11 +510,22 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
             const int b_first = __shfl_sync(0xffffffffu, b, l_first), b_last = __shfl_sync(0xffffffffu, b, l_last);
             bool staged = (a.mode == 0) && (r_first == r_last) && !__any_sync(0xffffffffu, live && edge);
             int ws[3] = {0, 0, 0}, wn[3] = {0, 0, 0};
+            int cs_s[3] = {0, 0, 0}, cs_e[3] = {0, 0, 0};           // this lane's three candidate ranges
             if (staged) {
+                // the window bounds and the lane's own range bounds are independent loads: all twelve are
+                // in flight together (they used to be four dependent round trips per unit)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     ws[k] = cs[(r_first + k - 1) * a.nbx + b_first - CL_K];
-                    wn[k] = cs[(r_first + k - 1) * a.nbx + b_last + CL_K + 1] - ws[k];
+                    wn[k] = cs[(r_first + k - 1) * a.nbx + b_last + CL_K + 1];
+                    if (live) {
+                        cs_s[k] = cs[(r + k - 1) * a.nbx + b - CL_K];
+                        cs_e[k] = cs[(r + k - 1) * a.nbx + b + CL_K + 1];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    wn[k] -= ws[k];
                     staged = staged && (wn[k] <= CL_WIN);
                 }
             }
@@ -497,10 +553,10 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
                 int nn = 0;                                             // neighbours appended so far
                 if (live) {
                     const float2 nri = make_float2(-ri.x, -ri.y);
-#pragma unroll 1
+#pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const int s = cs[(r + k - 1) * a.nbx + b - CL_K] - ws[k];
-                        const int e = cs[(r + k - 1) * a.nbx + b + CL_K + 1] - ws[k];
+                        const int s = cs_s[k] - ws[k];
+                        const int e = cs_e[k] - ws[k];
                         const float2* __restrict__ w = win + k * CL_WIN;
                         const int iself = (k == 1) ? i - ws[k] : -1;    // own slot (own row only)
 #pragma unroll 2
