@@ -561,16 +561,19 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
                         const int iself = (k == 1) ? i - ws[k] : -1;    // own slot (own row only)
 #pragma unroll 2
                         for (int t = s; t < e; t += 2) {
+                            // (slot t + 1 == e is read but never taken: it lies inside the staged buffer;
+                            //  one clamp per pair: the byte row has four bytes of slack)
                             const float2 d0 = __fadd2_rn(w[t], nri);
-                            const float2 d1 = __fadd2_rn(w[min(t + 1, e - 1)], nri);
+                            const float2 d1 = __fadd2_rn(w[t + 1], nri);
                             const float2 q0 = __fmul2_rn(d0, d0), q1 = __fmul2_rn(d1, d1);
                             const float r20 = __fadd_rn(q0.x, q0.y), r21 = __fadd_rn(q1.x, q1.y);
                             const bool in0 = (r20 < lim2) & (t != iself);
                             const bool in1 = (r21 < lim2) & (t + 1 < e) & (t + 1 != iself);
-                            myb[min(nn, 4 * CL_NW)] = (unsigned char)(k * CL_WIN + t);
-                            nn += in0 ? 1 : 0;
-                            myb[min(nn, 4 * CL_NW)] = (unsigned char)(k * CL_WIN + t + 1);
-                            nn += in1 ? 1 : 0;
+                            unsigned char* dst = myb + min(nn, 4 * CL_NW);
+                            const int a0 = in0 ? 1 : 0;
+                            dst[0] = (unsigned char)(k * CL_WIN + t);
+                            dst[a0] = (unsigned char)(k * CL_WIN + t + 1);
+                            nn += a0 + (in1 ? 1 : 0);
                         }
                     }
                 }
