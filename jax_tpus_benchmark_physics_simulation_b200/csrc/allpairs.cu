@@ -592,16 +592,6 @@ struct CluArgs {
 //     fp32 in the reference itself.  The energy variant (rare steps) keeps the exact index test.
 struct SliceSum { float2 fx, fy, pe; };
 
-__device__ __forceinline__ float set_ge_f32(float a, float b) {       // 1.0f if a >= b else 0.0f, in a register
-    float m;
-    asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(m) : "f"(a), "f"(b));
-    return m;
-}
-__device__ __forceinline__ float set_lt_f32(float a, float b) {
-    float m;
-    asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(m) : "f"(a), "f"(b));
-    return m;
-}
 __device__ __forceinline__ float min_image_bf(float d, float box, float timg) {
     return fmaf(-set_ge_f32(fabsf(d), timg), copysignf(box, d), d);
 }

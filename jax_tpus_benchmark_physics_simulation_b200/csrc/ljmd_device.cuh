@@ -10,6 +10,18 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 
+// compare results as 1.0f / 0.0f in a register (FSET.BF): predicate-free masks
+__device__ __forceinline__ float set_ge_f32(float a, float b) {       // 1.0f if a >= b else 0.0f, in a register
+    float m;
+    asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(m) : "f"(a), "f"(b));
+    return m;
+}
+__device__ __forceinline__ float set_lt_f32(float a, float b) {
+    float m;
+    asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(m) : "f"(a), "f"(b));
+    return m;
+}
+
 // minimum image, bit-identical to  d - box * round(d / box)  of MD:46-48 for |d| <= box
 // (see PairConsts::timg).  FSETP + LOP3 + predicated FADD.
 __device__ __forceinline__ float min_image(float d, float box, float timg) {
