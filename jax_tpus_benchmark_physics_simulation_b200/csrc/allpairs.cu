@@ -1,20 +1,20 @@
 // allpairs.cu — dense O(N^2) path: the reference's own formulation (MD:50-75) on B200.
 //
-// One PERSISTENT cooperative kernel runs a whole equilibrate_fn / production_fn call
-// (MD:77-106) without returning to the host:
+// Every kernel here is PERSISTENT: one launch runs a whole equilibrate_fn / production_fn call
+// (MD:77-106) without returning to the host.  Three kernels, chosen at create (ljmd_allpairs_mode):
 //
-//   per step   [b] partial forces  : the flattened (i-block x j) work is cut into gridDim.x
-//                                    equal contiguous ranges (stream-K style), so every SM
-//                                    sub-partition gets the same number of pair evaluations
-//                                    whatever N is; j positions are staged through shared
-//                                    memory, i positions and accumulators live in registers.
-//              grid barrier
-//              [d] reduce+integrate: the owner thread of particle g sums the partials of its
-//                                    i-block in a fixed order (deterministic, atomic-free),
-//                                    finishes the velocity-Verlet step, writes the sample /
-//                                    energies, and drifts the particle into the other
-//                                    position buffer (ping-pong) for the next step.
-//              grid barrier
+//   ap_cluster_kernel            N <= 640, one GPU: one thread-block cluster, positions in distributed
+//                                shared memory, velocities in registers, one cluster barrier per step.
+//   ap_persistent_kernel<3>      N >= 2048, one GPU: Newton's-third-law tiles (64 i x 32 j, the j particle
+//                                and its force travel around the warp by shuffle), patch partial vectors,
+//                                dynamic patch queue.
+//   ap_persistent_kernel<1|2>    everything else, and every multi-GPU run: ordered pairs, the flattened
+//                                (i-block x j) work cut into equal-cost contiguous ranges (stream-K style),
+//                                j positions staged through shared memory.
+//
+// The grid kernels run, per step:  [b] partial forces -> grid barrier -> [d] reduce the partials in a
+// fixed order (deterministic, atomic-free), finish the velocity-Verlet step, write the sample / energies,
+// drift into the other position buffer (ping-pong) -> grid barrier.
 //
 // F(R_new) of step n is carried to step n+1 (the reference recomputes it, bit-identically:
 // SURVEY.md §0), so there is one O(N^2) evaluation per step.  Each particle's state is read
@@ -68,7 +68,6 @@ struct ApArgs {
     float2*          part;        // [G*maxseg*BLOCK_I] partial forces
     // Newton's-third-law tile mode (IPT == 3): upper-triangular patches of Pt x Pt tiles of 64 x 64
     int              Pt, q, npr;  // patch edge in tiles, tiles per warp edge (Pt = 2q), patch rows
-    const int*       cta_pstart;  // (unused: patches are handed out dynamically)
     int              npatch, npe; // number of patches; number of energy partials per parity
     int*             sched;       // [2] patch counters (by step parity)
     const int2*      patches;     // (pa, pb) patch coordinates, pa <= pb
@@ -867,7 +866,6 @@ struct AllPairs {
     int ipt = 1, G = 0, NJu = 0, nI = 0, maxseg = 0;
     int Pt = 0, q = 0, npr = 0, npatch = 0, npe = 0;   // Newton's-third-law tile mode (ipt == 3)
     int* sched = nullptr;
-    int*  d_cta_pstart = nullptr;
     int2* d_patches = nullptr;
     float2 *rowpart = nullptr, *colpart = nullptr;
     long long* d_cta_start = nullptr;
@@ -960,7 +958,6 @@ int ap_create(ljmd_handle* h) {
     long long g_work = std::max<long long>(1, W / (64 / J_UNIT));
     ap->G = (int)std::min<long long>((long long)per_sm * h->num_sms, std::min(g_work, W));
     if (const char* e = getenv("LJMD_AP_GRID")) ap->G = std::max(1, std::min(atoi(e), ap->G));
-    std::vector<int> pstart;
     std::vector<int2> patches;
     if (ap->ipt == 3) {
         // upper-triangular patches of Pt x Pt tiles (tile = 64 x 64 particles); a CTA's 2 x 2 warps take
@@ -982,8 +979,6 @@ int ap_create(ljmd_handle* h) {
         ap->npatch = (int)npatch;
         ap->G = (int)std::min<long long>(slots, npatch);
         if (const char* e = getenv("LJMD_AP_GRID")) ap->G = std::max(1, std::min(atoi(e), ap->G));
-        pstart.resize(ap->G + 1);
-        for (int c = 0; c <= ap->G; ++c) pstart[c] = (int)(npatch * c / ap->G);
     }
 
     // stream-K split of the flattened (i-block, j-unit) space, by COST: a j unit that overlaps
@@ -1068,9 +1063,7 @@ int ap_create(ljmd_handle* h) {
     LJ_CUDA(cudaMalloc(&ap->part, sizeof(float2) * (size_t)ap->G * ap->maxseg * BI));
     if (ap->ipt == 3) {
         const size_t np = patches.size(), ps = (size_t)ap->Pt * T3_BLK;
-        LJ_CUDA(cudaMalloc(&ap->d_cta_pstart, sizeof(int) * pstart.size()));
         LJ_CUDA(cudaMalloc(&ap->d_patches, sizeof(int2) * np));
-        LJ_CUDA(cudaMemcpy(ap->d_cta_pstart, pstart.data(), sizeof(int) * pstart.size(), cudaMemcpyHostToDevice));
         LJ_CUDA(cudaMemcpy(ap->d_patches, patches.data(), sizeof(int2) * np, cudaMemcpyHostToDevice));
         LJ_CUDA(cudaMalloc(&ap->rowpart, sizeof(float2) * np * ps));
         LJ_CUDA(cudaMalloc(&ap->colpart, sizeof(float2) * np * ps));
@@ -1092,7 +1085,7 @@ void ap_destroy(ljmd_handle* h) {
     cudaFree(ap->d_cta_start); cudaFree(ap->d_cta_ib0); cudaFree(ap->d_iblk);
     cudaFree(ap->shared); cudaFree(ap->Vh); cudaFree(ap->Ftmp);
     cudaFree(ap->part); cudaFree(ap->pe_part); cudaFree(ap->ke_part);
-    cudaFree(ap->d_cta_pstart); cudaFree(ap->d_patches); cudaFree(ap->rowpart); cudaFree(ap->colpart);
+    cudaFree(ap->d_patches); cudaFree(ap->rowpart); cudaFree(ap->colpart);
     cudaFree(ap->sched);
     cudaFree(ap->bar); cudaFree(ap->err);
     delete ap;
@@ -1121,7 +1114,7 @@ int ap_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_out
     a.R_in = R_in; a.Rbuf0 = ap->Rbuf0; a.Rbuf1 = ap->Rbuf1; a.Vh = ap->Vh; a.Ftmp = ap->Ftmp;
     a.part = ap->part; a.pe_part = ap->pe_part; a.ke_part = ap->ke_part;
     a.Pt = ap->Pt; a.q = ap->q; a.npr = ap->npr; a.npatch = ap->npatch; a.npe = ap->npe; a.sched = ap->sched;
-    a.cta_pstart = ap->d_cta_pstart; a.patches = ap->d_patches; a.rowpart = ap->rowpart; a.colpart = ap->colpart;
+    a.patches = ap->d_patches; a.rowpart = ap->rowpart; a.colpart = ap->colpart;
     a.bar = ap->bar; a.err = ap->err; a.prof = ap->prof;
     a.rc = rc;
     a.R_out = R_out; a.V_out = V_out; a.F_out = F_out; a.pe_out = pe_out;

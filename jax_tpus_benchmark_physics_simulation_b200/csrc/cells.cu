@@ -640,10 +640,6 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
     CL_PROF(7);
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
-
 // ---- per-step pass ----------------------------------------------------------------------------------
 // Two neighbours j0, j1 of ONE particle.  Each displacement (dx, dy) is one packed FP32x2 value made
 // directly from the loaded float2 (no register shuffling); from r2 on, the two NEIGHBOURS share the
@@ -723,27 +719,6 @@ __device__ __forceinline__ void word_eval(const PairConsts& pc, const PairConsts
     const float2 r2 = win[(word >> 16) & 0xffu], r3 = win[word >> 24];
     eval_two<PE, false>(pc, c2, nri, r0, r1, true, acc, pe2);
     eval_two<PE, false>(pc, c2, nri, r2, r3, true, acc, pe2);
-}
-
-template <bool PE>
-__device__ __forceinline__ void bytes_force(const CellsArgs& a, const float2* win, int i, int nw, float2 ri,
-                                            float& Fx, float& Fy, float& pe) {
-    const PairConsts pc = a.pc;
-    const PairConsts2 c2 = make_pair_consts2(pc);
-    const unsigned* __restrict__ np = a.nb4 + i;
-    const size_t stride = (size_t)a.Nalloc;
-    unsigned w[CL_NWPRE];
-#pragma unroll
-    for (int u = 0; u < CL_NWPRE; ++u) w[u] = (u < nw) ? np[(size_t)u * stride] : 0xffffffffu;
-    const float2 nri = make_float2(-ri.x, -ri.y);
-    float2 acc = make_float2(0.0f, 0.0f), pe2 = acc;
-#pragma unroll
-    for (int u = 0; u < CL_NWPRE; ++u)
-        if (u < nw) word_eval<PE>(pc, c2, win, w[u], nri, acc, pe2);          // warp-uniform
-    for (int u = CL_NWPRE; u < nw; ++u) word_eval<PE>(pc, c2, win, np[(size_t)u * stride], nri, acc, pe2);
-    Fx = -acc.x;
-    Fy = -acc.y;
-    if (PE) pe = pe2.x + pe2.y;
 }
 
 // ---- cp.async (LDGSTS) helpers: global -> shared without passing through registers ------------------
