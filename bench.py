@@ -401,11 +401,11 @@ def main():
             roofline["gathered_bytes_per_particle_step"] = BYTES_PER_PARTICLE_STEP + n_list * (1.0 + 8.0)
             roofline["gathered_GBps"] = roofline["gathered_bytes_per_particle_step"] * per_s / 1e9
             if wl_name == "cells4m":
-                # dram__bytes_read.sum + dram__bytes_write.sum of profiles/r1_cells4m_cpasync_v4.ncu-rep
-                # (same N, skin; 30 steps incl. the first sort): 10.28 GB / (30 x 4,194,304) particle-steps
-                roofline["traffic"] = 81.7 * N * md_steps
-                roofline["traffic_source"] = ("81.7 B per particle-step measured by ncu --set full on a 30-step "
-                                              "launch (profiles/r1_cells4m_cpasync_v4.ncu-rep), scaled to this launch")
+                # dram__bytes_read.sum + dram__bytes_write.sum of profiles/r1_cells4m_final.ncu-rep
+                # (same N, skin; 30 steps incl. the first sort): 10.25 GB / (30 x 4,194,304) particle-steps
+                roofline["traffic"] = 81.5 * N * md_steps
+                roofline["traffic_source"] = ("81.5 B per particle-step measured by ncu --set full on a 30-step "
+                                              "launch (profiles/r1_cells4m_final.ncu-rep), scaled to this launch")
 
     # ---- CPU baseline: bounded sample of the same workload on this box's host cores ------------
     cpu_baseline = None
