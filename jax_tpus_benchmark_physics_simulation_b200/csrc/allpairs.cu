@@ -71,6 +71,12 @@ struct ApArgs {
     int              npatch, npe; // number of patches; number of energy partials per parity
     int*             sched;       // [2] patch counters (by step parity)
     const int2*      patches;     // (pa, pb) patch coordinates, pa <= pb
+    // tile mode on several GPUs: the patches are dealt to the ranks; a rank sums ITS partial vectors into one
+    // partial force per particle of the WHOLE system and stores it into the owner's receive buffer
+    // (a reduce-scatter made of NVLink peer stores), the owner adds the P contributions in rank order
+    const int*       blk_off;     // [npr+1] CSR over blocks of Pt*64 particles ...
+    const int*       blk_ent;     // ... of (local patch index * 2 + side), side 0 = row, 1 = column
+    float2*          peerF[LJMD_MAX_RANKS];   // every rank's receive buffer [P][Nloc]
     float2*          rowpart;     // [npatch][Pt*64] partial force on the patch's row (i) side
     float2*          colpart;     // [npatch][Pt*64] partial force on the patch's column (j) side
     float*           pe_part;     // [2*G] per-CTA partial potential energy (by step parity)
@@ -252,7 +258,9 @@ __device__ __forceinline__ void ap3_phase_forces(const ApArgs& a, const float2* 
         if (pi >= a.npatch) break;
         float pe_thread = 0.0f;
         const int2 pp = a.patches[pi];
-        const int pid = tri_base(pp.x, a.npr) + (pp.y - pp.x);
+        // the partial vectors are indexed by position in the patch list (on one GPU the list is the whole
+        // triangle in (pa, pb) order: that index is tri_base(pa) + pb - pa, which the reduction relies on)
+        const int pid = pi;
         for (int k = lane; k < q * T3_BLK; k += 32) colacc[k] = make_float2(0.0f, 0.0f);
         __syncwarp();
         for (int r = 0; r < q; ++r) {
@@ -386,6 +394,64 @@ ap_persistent_kernel(const ApArgs a) {
         if (prof) { long long t = clock64(); pt[0] += t - pt[4]; pt[4] = t; }
         grid_barrier(a.bar, (++epoch) * (unsigned)a.G, a.err);
         if (prof) { long long t = clock64(); pt[1] += t - pt[4]; pt[4] = t; }
+        // cross-GPU epochs of this step (tile mode on several GPUs uses two: partial forces, positions)
+        const unsigned xper = (V3 && a.P > 1) ? 2u : 1u;
+        const unsigned xe0 = a.xepoch0 + xper * (unsigned)(s - a.s_begin);
+        auto peer_wait = [&](unsigned xe) {
+            // every rank's peer stores of this phase have landed once all P arrival words carry the epoch
+            if (c == 0 && tid < a.P && tid != a.rank) {
+                __threadfence_system();
+                volatile unsigned* f = a.peer_flags[tid] + a.rank;
+                *f = xe;
+            }
+            if (tid == 0) {
+                const volatile unsigned* mine = a.peer_flags[a.rank];
+                long long t0 = clock64();
+                for (int q = 0; q < a.P; ++q) {
+                    if (q == a.rank) continue;
+                    while ((int)(mine[q] - xe) < 0) {
+                        if (clock64() - t0 > (1ll << 33)) { atomicExch(a.err, 2); break; }
+                    }
+                }
+                __threadfence_system();
+            }
+            __syncthreads();
+        };
+        if constexpr (V3) {
+            if (a.P > 1) {
+                // ---- [c] this rank's partial force on EVERY particle -> the owner's receive buffer --------
+                const int bsz = a.Pt * T3_BLK;
+                const int grp_c = tid / RED_LANES, gl_c = tid % RED_LANES;
+                for (int gb = c * (AP_THREADS / RED_LANES); gb < a.N; gb += a.G * (AP_THREADS / RED_LANES)) {
+                    const int g = gb + grp_c;
+                    const bool live = g < a.N;
+                    float Fx = 0.0f, Fy = 0.0f;
+                    if (live) {
+                        const int blk = g / bsz;
+                        const size_t off = (size_t)(g - blk * bsz);
+                        const int e1 = a.blk_off[blk + 1];
+                        for (int e = a.blk_off[blk] + gl_c; e < e1; e += RED_LANES) {
+                            const int ent = a.blk_ent[e];
+                            const float2* base = (ent & 1) ? a.colpart : a.rowpart;
+                            const float2 pv = __ldcg(base + (size_t)(ent >> 1) * bsz + off);
+                            Fx += pv.x; Fy += pv.y;
+                        }
+                    }
+#pragma unroll
+                    for (int o = RED_LANES / 2; o > 0; o >>= 1) {
+                        Fx += __shfl_xor_sync(0xffffffffu, Fx, o);
+                        Fy += __shfl_xor_sync(0xffffffffu, Fy, o);
+                    }
+                    if (live && gl_c == 0) {
+                        const int owner = g / a.Nloc;
+                        a.peerF[owner][(size_t)a.rank * a.Nloc + (g - owner * a.Nloc)] = make_float2(Fx, Fy);
+                    }
+                }
+                __threadfence_system();
+                grid_barrier(a.bar, (++epoch) * (unsigned)a.G, a.err);
+                peer_wait(xe0 + 1u);
+            }
+        }
 
         // ---- [d] reduce partials, finish the velocity-Verlet step -----------------------------
         // CTA c owns particles [c*ppc, (c+1)*ppc); a group of RED_LANES lanes sums the partials of
@@ -405,7 +471,13 @@ ap_persistent_kernel(const ApArgs a) {
                 if (rc.nsteps > 0) v = a.Vh[g];
             }
             if (live) {
-                if constexpr (V3) {
+                if (V3 && a.P > 1) {
+                    // the P ranks' partial forces on my particle (rank order, then the fixed shuffle tree)
+                    for (int t = gl; t < a.P; t += RED_LANES) {
+                        const float2 pv = __ldcg(&a.peerF[a.rank][(size_t)t * a.Nloc + gloc]);
+                        Fx += pv.x; Fy += pv.y;
+                    }
+                } else if constexpr (V3) {
                     // row-side partials of patches (pr, pb >= pr), then column-side of (pa <= pr, pr)
                     const int blk = g / T3_BLK, pr = blk / a.Pt;
                     const size_t off = (size_t)(blk - pr * a.Pt) * T3_BLK + (g - blk * T3_BLK);
@@ -505,26 +577,9 @@ ap_persistent_kernel(const ApArgs a) {
         if (prof) { long long t = clock64(); pt[2] += t - pt[4]; pt[4] = t; }
         grid_barrier(a.bar, (++epoch) * (unsigned)a.G, a.err);
         if (a.P > 1 && !final) {
-            // every rank has pushed its slab into our next-position buffer once all P arrival words
-            // carry this epoch: one NVLink round trip per step, no NCCL on the step path
-            const unsigned xe = a.xepoch0 + (unsigned)(s - a.s_begin) + 1u;
-            if (c == 0 && tid < a.P && tid != a.rank) {
-                __threadfence_system();
-                volatile unsigned* f = a.peer_flags[tid] + a.rank;
-                *f = xe;
-            }
-            if (tid == 0) {
-                const volatile unsigned* mine = a.peer_flags[a.rank];
-                long long t0 = clock64();
-                for (int q = 0; q < a.P; ++q) {
-                    if (q == a.rank) continue;
-                    while ((int)(mine[q] - xe) < 0) {
-                        if (clock64() - t0 > (1ll << 33)) { atomicExch(a.err, 2); break; }
-                    }
-                }
-                __threadfence_system();
-            }
-            __syncthreads();
+            // every rank has pushed its slab into our next-position buffer: one NVLink round trip per step,
+            // no NCCL on the step path
+            peer_wait(xe0 + xper);
         }
         if (prof) { long long t = clock64(); pt[3] += t - pt[4]; pt[4] = t; }
 
@@ -867,6 +922,8 @@ struct AllPairs {
     int Pt = 0, q = 0, npr = 0, npatch = 0, npe = 0;   // Newton's-third-law tile mode (ipt == 3)
     int* sched = nullptr;
     int2* d_patches = nullptr;
+    int *d_blk_off = nullptr, *d_blk_ent = nullptr;     // tile mode on several GPUs: per-block partial lists
+    float2* peerF[LJMD_MAX_RANKS] = {};                 //   and every rank's receive buffer
     float2 *rowpart = nullptr, *colpart = nullptr;
     long long* d_cta_start = nullptr;
     int*       d_cta_ib0 = nullptr;
@@ -935,9 +992,11 @@ int ap_create(ljmd_handle* h) {
     const long long N = h->p.N;
     const int P = std::max(1, h->nranks);
     // ipt 1 / 2: ordered pairs, one / two i per thread (stream-K split, any rank count);
-    // ipt 3: Newton's-third-law tiles (each unordered pair once, single GPU)
-    ap->ipt = (N >= 2048) ? ((P == 1) ? 3 : 2) : 1;
-    if (const char* e = getenv("LJMD_AP_IPT")) { const int v = atoi(e); if (v >= 1 && v <= 3 && (v != 3 || P == 1)) ap->ipt = v; }
+    // ipt 3: Newton's-third-law tiles (each unordered pair once); on several GPUs the patches are dealt to
+    //        the ranks and the partial forces are reduce-scattered over NVLink
+    ap->ipt = (N >= 2048) ? 3 : 1;
+    if (P > 1 && N / P < 2048) ap->ipt = (N >= 2048) ? 2 : 1;     // too few patches per rank for the tile mode
+    if (const char* e = getenv("LJMD_AP_IPT")) { const int v = atoi(e); if (v >= 1 && v <= 3 && (v != 3 || P == 1 || ap->ipt == 3)) ap->ipt = v; }
     const int BI = AP_THREADS * (ap->ipt == 3 ? 1 : ap->ipt);
     if (N % P != 0) { set_error("all-pairs atom decomposition needs N divisible by the rank count"); return LJMD_E_INVALID; }
     ap->Nloc = (int)(N / P);
@@ -959,6 +1018,7 @@ int ap_create(ljmd_handle* h) {
     ap->G = (int)std::min<long long>((long long)per_sm * h->num_sms, std::min(g_work, W));
     if (const char* e = getenv("LJMD_AP_GRID")) ap->G = std::max(1, std::min(atoi(e), ap->G));
     std::vector<int2> patches;
+    std::vector<int> blk_off, blk_ent;
     if (ap->ipt == 3) {
         // upper-triangular patches of Pt x Pt tiles (tile = 64 x 64 particles); a CTA's 2 x 2 warps take
         // q x q tiles each (Pt = 2q).  A diagonal patch does half the work of an off-diagonal one but
@@ -968,13 +1028,28 @@ int ap_create(ljmd_handle* h) {
         int q = 8;
         for (; q > 1; q >>= 1) {
             const long long npr = (blocks + 2 * q - 1) / (2 * q);
-            if (npr * (npr + 1) / 2 >= 4 * slots) break;          // enough patches to balance
+            if (npr * (npr + 1) / 2 / P >= 4 * slots) break;      // enough patches (per rank) to balance
         }
         if (const char* e = getenv("LJMD_AP_Q")) q = std::max(1, std::min(8, atoi(e)));
         ap->q = q; ap->Pt = 2 * q;
         ap->npr = (blocks + ap->Pt - 1) / ap->Pt;
-        for (int pa = 0; pa < ap->npr; ++pa)
-            for (int pb = pa; pb < ap->npr; ++pb) patches.push_back(make_int2(pa, pb));
+        // several GPUs: the triangle's patches are dealt to the ranks round-robin (diagonal patches, which
+        // cost half, are spread evenly that way); a rank's partial vectors are indexed by its own list
+        {
+            long long k = 0;
+            for (int pa = 0; pa < ap->npr; ++pa)
+                for (int pb = pa; pb < ap->npr; ++pb, ++k)
+                    if (k % P == h->rank) patches.push_back(make_int2(pa, pb));
+        }
+        if (P > 1) {
+            blk_off.assign(ap->npr + 1, 0);
+            for (size_t lp = 0; lp < patches.size(); ++lp) { blk_off[patches[lp].x + 1]++; blk_off[patches[lp].y + 1]++; }
+            for (int b = 0; b < ap->npr; ++b) blk_off[b + 1] += blk_off[b];
+            blk_ent.resize(blk_off[ap->npr]);
+            std::vector<int> fill(blk_off.begin(), blk_off.end() - 1);
+            for (size_t lp = 0; lp < patches.size(); ++lp) blk_ent[fill[patches[lp].x]++] = (int)lp * 2;        // row side
+            for (size_t lp = 0; lp < patches.size(); ++lp) blk_ent[fill[patches[lp].y]++] = (int)lp * 2 + 1;    // column side
+        }
         const long long npatch = (long long)patches.size();
         ap->npatch = (int)npatch;
         ap->G = (int)std::min<long long>(slots, npatch);
@@ -1038,7 +1113,7 @@ int ap_create(ljmd_handle* h) {
     LJ_CUDA(cudaMemcpy(ap->d_iblk, iblk.data(), sizeof(int2) * ap->nI, cudaMemcpyHostToDevice));
     {   // one >= 2 MiB allocation so that its IPC handle maps exactly this region on the peers
         const size_t rb = (sizeof(float2) * (size_t)N + 255) / 256 * 256;
-        size_t bytes = 2 * rb + 256;
+        size_t bytes = 2 * rb + 256 + rb;          // Rbuf0 | Rbuf1 | arrival words | receive buffer [P][Nloc]
         bytes = std::max<size_t>((bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20), 4u << 20);
         LJ_CUDA(cudaMalloc(&ap->shared, bytes));
         LJ_CUDA(cudaMemset(ap->shared, 0, bytes));
@@ -1046,6 +1121,7 @@ int ap_create(ljmd_handle* h) {
         ap->Rbuf1 = reinterpret_cast<float2*>(reinterpret_cast<char*>(ap->shared) + rb);
         ap->xflags = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ap->shared) + 2 * rb);
         ap->peerR0[h->rank] = ap->Rbuf0; ap->peerR1[h->rank] = ap->Rbuf1; ap->peer_flags[h->rank] = ap->xflags;
+        ap->peerF[h->rank] = reinterpret_cast<float2*>(reinterpret_cast<char*>(ap->shared) + 2 * rb + 256);
         if (P > 1) {
             void* peers[LJMD_MAX_RANKS];
             int r = dist_share(h, ap->shared, peers);
@@ -1055,6 +1131,7 @@ int ap_create(ljmd_handle* h) {
                 ap->peerR0[q] = reinterpret_cast<float2*>(base);
                 ap->peerR1[q] = reinterpret_cast<float2*>(base + rb);
                 ap->peer_flags[q] = reinterpret_cast<unsigned*>(base + 2 * rb);
+                ap->peerF[q] = reinterpret_cast<float2*>(base + 2 * rb + 256);
             }
         }
     }
@@ -1065,6 +1142,12 @@ int ap_create(ljmd_handle* h) {
         const size_t np = patches.size(), ps = (size_t)ap->Pt * T3_BLK;
         LJ_CUDA(cudaMalloc(&ap->d_patches, sizeof(int2) * np));
         LJ_CUDA(cudaMemcpy(ap->d_patches, patches.data(), sizeof(int2) * np, cudaMemcpyHostToDevice));
+        if (!blk_ent.empty()) {
+            LJ_CUDA(cudaMalloc(&ap->d_blk_off, sizeof(int) * blk_off.size()));
+            LJ_CUDA(cudaMalloc(&ap->d_blk_ent, sizeof(int) * blk_ent.size()));
+            LJ_CUDA(cudaMemcpy(ap->d_blk_off, blk_off.data(), sizeof(int) * blk_off.size(), cudaMemcpyHostToDevice));
+            LJ_CUDA(cudaMemcpy(ap->d_blk_ent, blk_ent.data(), sizeof(int) * blk_ent.size(), cudaMemcpyHostToDevice));
+        }
         LJ_CUDA(cudaMalloc(&ap->rowpart, sizeof(float2) * np * ps));
         LJ_CUDA(cudaMalloc(&ap->colpart, sizeof(float2) * np * ps));
     }
@@ -1085,7 +1168,7 @@ void ap_destroy(ljmd_handle* h) {
     cudaFree(ap->d_cta_start); cudaFree(ap->d_cta_ib0); cudaFree(ap->d_iblk);
     cudaFree(ap->shared); cudaFree(ap->Vh); cudaFree(ap->Ftmp);
     cudaFree(ap->part); cudaFree(ap->pe_part); cudaFree(ap->ke_part);
-    cudaFree(ap->d_patches); cudaFree(ap->rowpart); cudaFree(ap->colpart);
+    cudaFree(ap->d_patches); cudaFree(ap->d_blk_off); cudaFree(ap->d_blk_ent); cudaFree(ap->rowpart); cudaFree(ap->colpart);
     cudaFree(ap->sched);
     cudaFree(ap->bar); cudaFree(ap->err);
     delete ap;
@@ -1106,7 +1189,8 @@ int ap_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_out
     a.pc = h->pc;
     a.ppc = (ap->Nloc + ap->G - 1) / ap->G;
     a.i_lo = ap->i_lo; a.Nloc = ap->Nloc; a.rank = h->rank; a.P = std::max(1, h->nranks);
-    for (int q = 0; q < LJMD_MAX_RANKS; ++q) { a.peerR0[q] = ap->peerR0[q]; a.peerR1[q] = ap->peerR1[q]; a.peer_flags[q] = ap->peer_flags[q]; }
+    for (int q = 0; q < LJMD_MAX_RANKS; ++q) { a.peerR0[q] = ap->peerR0[q]; a.peerR1[q] = ap->peerR1[q]; a.peer_flags[q] = ap->peer_flags[q]; a.peerF[q] = ap->peerF[q]; }
+    a.blk_off = ap->d_blk_off; a.blk_ent = ap->d_blk_ent;
     if (a.P > 1 && rc.thermo_every > 0) { set_error("the rescale thermostat is single-GPU only"); return LJMD_E_UNSUPPORTED; }
     a.N = (int)N; a.G = ap->G; a.NJu = ap->NJu; a.nI = ap->nI; a.maxseg = ap->maxseg;
     a.dt = h->p.dt;
@@ -1174,7 +1258,7 @@ int ap_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_out
         void* args[] = {(void*)&a};
         LJ_CUDA(cudaLaunchCooperativeKernel((void*)ap->kernel, dim3(ap->G), dim3(AP_THREADS), args, 0, st));
         h->launches++;
-        ap->xepoch += (unsigned)(e - s);             // one cross-GPU epoch per step of the launch
+        ap->xepoch += (unsigned)(e - s) * ((ap->ipt == 3 && a.P > 1) ? 2u : 1u);   // cross-GPU epochs per step
         s = e;
     }
     if (a.P > 1) {
