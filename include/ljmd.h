@@ -124,8 +124,9 @@ int ljmd_last_rebuilds(ljmd_t* h, int64_t* rebuilds);
 /* ---- multi-GPU (new; the reference is single-device) ---------------------------- */
 /* One handle per rank/device.  nccl_unique_id: the 128 bytes of an ncclUniqueId made
  * by rank 0 and broadcast by the caller (e.g. over torch.distributed/gloo).
- * Atom decomposition for all-pairs (position exchange each step), row-slab
- * decomposition with halo-row exchange for the cell list (both as in-kernel NVLink peer
+ * Atom decomposition for all-pairs (position all-gather each step, plus a reduce-scatter
+ * of partial forces when the Newton's-third-law tiles are dealt to the ranks), row-slab
+ * decomposition with halo-row exchange for the cell list (all as in-kernel NVLink peer
  * stores); one all-reduce for energies.  Cell list on several GPUs: no thermostat, outputs
  * must not alias inputs, neighbor_count is single-GPU.
  * R/V arguments of ljmd_run etc. are then the FULL (N,2) arrays on every rank
@@ -140,7 +141,7 @@ int ljmd_create_dist(ljmd_t** out, const ljmd_params* p, const void* nccl_unique
 int ljmd_last_run_ms(ljmd_t* h, float* ms);
 /* all-pairs evaluation mode chosen at create: 1 / 2 = every ORDERED pair is evaluated (one / two
  * i-particles per thread), 3 = Newton's-third-law tiles: every UNORDERED pair is evaluated once and
- * applied to both particles (atomic-free; single GPU, N >= 2048), 4 = ordered pairs inside ONE
+ * applied to both particles (atomic-free; N >= 2048, slabs of >= 2048 particles per GPU), 4 = ordered pairs inside ONE
  * thread-block cluster with the state resident in distributed shared memory (single GPU, N <= 640).
  * 0 on the cell-list path.                                                                        */
 int ljmd_allpairs_mode(ljmd_t* h, int32_t* mode);

@@ -5,10 +5,11 @@
 //
 //   ap_cluster_kernel            N <= 640, one GPU: one thread-block cluster, positions in distributed
 //                                shared memory, velocities in registers, one cluster barrier per step.
-//   ap_persistent_kernel<3>      N >= 2048, one GPU: Newton's-third-law tiles (64 i x 32 j, the j particle
-//                                and its force travel around the warp by shuffle), patch partial vectors,
-//                                dynamic patch queue.
-//   ap_persistent_kernel<1|2>    everything else, and every multi-GPU run: ordered pairs, the flattened
+//   ap_persistent_kernel<3>      N >= 2048: Newton's-third-law tiles (64 i x 32 j, the j particle and its
+//                                force travel around the warp by shuffle), patch partial vectors, dynamic
+//                                patch queue; on several GPUs the patches are dealt to the ranks and the
+//                                partial forces are reduce-scattered with NVLink peer stores.
+//   ap_persistent_kernel<1|2>    everything else: ordered pairs, the flattened
 //                                (i-block x j) work cut into equal-cost contiguous ranges (stream-K style),
 //                                j positions staged through shared memory.
 //
