@@ -919,7 +919,6 @@ extern __shared__ __align__(16) unsigned char cells_smem[];
 __global__ void __launch_bounds__(CL_THREADS, 2)
 cells_persistent_kernel(const CellsArgs a) {
     __shared__ int    sscan[CL_THREADS / 32 + 1];
-    __shared__ float  sred[CL_THREADS / 32];
     __shared__ double sdbl[CL_THREADS / 32];
     __shared__ float  s_lambda;
     __shared__ long long s_pt[12];
