@@ -38,6 +38,8 @@ extern "C" {
 #define LJMD_E_NCCL      (-3)   /* NCCL failure (see ljmd_last_error)             */
 #define LJMD_E_NOMEM     (-4)
 #define LJMD_E_UNSUPPORTED (-5)
+#define LJMD_E_OVERFLOW  (-6)   /* device flag: neighbour list / slab capacity exceeded - results invalid */
+#define LJMD_E_TIMEOUT   (-7)   /* device flag: a grid barrier or cross-GPU wait timed out - results invalid */
 
 /* force-path selection */
 #define LJMD_PATH_AUTO      0   /* all-pairs for N <= 131072, else cell list      */
@@ -63,6 +65,12 @@ typedef struct ljmd_params {
 int         ljmd_abi_version(void);
 const char* ljmd_last_error(void);
 
+/* Positions handed to ljmd_energy / ljmd_forces / ljmd_run / ljmd_neighbor_count may lie anywhere:
+ * coordinates outside the closed interval [0, box] are wrapped with jnp.mod semantics (MD:72) when
+ * they are loaded (the reference's closures are periodic in R, MD:46-48), coordinates inside it
+ * - everything a previous step can produce - are used bit for bit.  ljmd_gr_hist and
+ * ljmd_cell_assign expect positions in [0, box] (what production_fn returns).                    */
+
 /* closure capture of N, box_size, sigma, epsilon, dt (MD:16-31).  All scratch
  * (partial sums, cell arrays, ping-pong state) is allocated here, never per call. */
 int  ljmd_create(ljmd_t** out, const ljmd_params* p);
@@ -85,6 +93,8 @@ int ljmd_forces(ljmd_t* h, const float* R, float* F, float* pe_dev);
  *   energy_every > 0 and ke_pe != NULL: after step i, if i % energy_every == 0,
  *     ke_pe[i / energy_every] = {KE, PE} of the post-step state
  *     (KE = 0.5*sum|V|^2, PE = total_energy_fn(R)); buffer is (ceil(nsteps/energy_every),2).
+ *     On a step that also rescales (thermostat), KE is the value BEFORE the rescale (the one the
+ *     rescale factor is computed from); the returned V is after it.
  *     Not in the reference (it never reports energies) — see DESIGN.md.
  *   thermostat_kT > 0: velocity-rescale thermostat, V *= sqrt(kT_target / (KE/N)) after every
  *     `thermostat_every`-th step.  Default off (<= 0) = the reference's pure NVE.
@@ -135,9 +145,21 @@ int ljmd_get_unique_id(void* id128);
 int ljmd_create_dist(ljmd_t** out, const ljmd_params* p, const void* nccl_unique_id,
                      int32_t rank, int32_t nranks);
 
+/* ---- run status -------------------------------------------------------------------- */
+/* The calls above only ENQUEUE work (JAX-style async dispatch), so conditions that a persistent
+ * kernel detects on the device cannot come back through their return value: a Verlet list or a
+ * slab that overflowed its buffers (LJMD_E_OVERFLOW: too dense for rc + skin, or too uneven over
+ * the GPUs), a grid barrier or a cross-GPU wait that timed out (LJMD_E_TIMEOUT).  ljmd_check blocks
+ * until everything enqueued on the handle's stream has finished and returns 0, a cudaError_t, or
+ * one of those codes for the most recent call (the flags are cleared when a call starts).  The
+ * outputs of a call that failed the check are invalid.  This is what block_until_ready (MD:145,
+ * 152,163) maps to in the host wrapper.  Spin waits give up after LJMD_SPIN_TIMEOUT_S seconds
+ * (environment, default 4; 0 = never: for cuda-gdb / compute-sanitizer sessions).              */
+int ljmd_check(ljmd_t* h);
+
 /* ---- measurement helpers --------------------------------------------------------- */
 /* device time (ms) of the last ljmd_run's step loop, measured with CUDA events on the
- * handle's stream (blocks until that run has finished).                             */
+ * handle's stream (blocks until that run has finished; also performs ljmd_check).   */
 int ljmd_last_run_ms(ljmd_t* h, float* ms);
 /* all-pairs evaluation mode chosen at create: 1 / 2 = every ORDERED pair is evaluated (one / two
  * i-particles per thread), 3 = Newton's-third-law tiles: every UNORDERED pair is evaluated once and

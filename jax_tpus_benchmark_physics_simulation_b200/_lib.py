@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LJMD_LIB", os.path.join(_HERE, "libljmd.so"))   # LJMD_LIB: developer override
 
 LJMD_PATH_AUTO, LJMD_PATH_ALLPAIRS, LJMD_PATH_CELLS = 0, 1, 2
+LJMD_E_OVERFLOW, LJMD_E_TIMEOUT = -6, -7
 
 # every symbol include/ljmd.h declares (checked by tests/test_abi.py)
 EXPORTS = (
@@ -20,6 +21,7 @@ EXPORTS = (
     "ljmd_forces", "ljmd_run", "ljmd_gr_hist", "ljmd_cell_geometry", "ljmd_cell_assign",
     "ljmd_neighbor_count", "ljmd_last_rebuilds", "ljmd_get_unique_id", "ljmd_create_dist",
     "ljmd_last_run_ms", "ljmd_launch_count", "ljmd_fp32_peak_probe", "ljmd_allpairs_mode",
+    "ljmd_check",
 )
 
 
@@ -40,7 +42,11 @@ class LjmdParams(ctypes.Structure):
 
 
 class LjmdError(RuntimeError):
-    pass
+    """A call of the C ABI failed; ``code`` is its return value (LJMD_E_* / cudaError_t)."""
+
+    def __init__(self, msg, code=None):
+        super().__init__(msg)
+        self.code = code
 
 
 _lib = None
@@ -75,6 +81,7 @@ def load() -> ctypes.CDLL:
     lib.ljmd_last_rebuilds.argtypes = [vp, ctypes.POINTER(i64)]
     lib.ljmd_get_unique_id.argtypes = [vp]
     lib.ljmd_create_dist.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(LjmdParams), vp, i32, i32]
+    lib.ljmd_check.argtypes = [vp]
     lib.ljmd_last_run_ms.argtypes = [vp, ctypes.POINTER(f32)]
     lib.ljmd_launch_count.argtypes = [vp, ctypes.POINTER(i64)]
     lib.ljmd_allpairs_mode.argtypes = [vp, ctypes.POINTER(i32)]
@@ -90,4 +97,4 @@ def load() -> ctypes.CDLL:
 def check(code: int, what: str) -> None:
     if code != 0:
         msg = load().ljmd_last_error().decode("utf-8", "replace")
-        raise LjmdError(f"{what} failed with code {code}: {msg}")
+        raise LjmdError(f"{what} failed with code {code}: {msg}", code)

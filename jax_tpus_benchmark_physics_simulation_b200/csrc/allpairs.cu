@@ -86,6 +86,7 @@ struct ApArgs {
     int*             err;
     long long*       prof;        // optional [G][4] phase clocks (debug: LJMD_AP_PROF=1)
     long long        s_begin, s_end;   // steps [s_begin, s_end); s = -1 is the prologue force
+    long long        spin_limit;       // clocks a spin wait may last (0 = unlimited)
     RunCtl           rc;
     float2*          R_out;
     float2*          V_out;
@@ -370,7 +371,8 @@ ap_persistent_kernel(const ApArgs a) {
     if (prof) { pt[0] = pt[1] = pt[2] = pt[3] = 0; }
 
     for (long long s = a.s_begin; s < a.s_end; ++s) {
-        const float2* Rcur  = (s < 0) ? a.R_in : ((s & 1) ? a.Rbuf1 : a.Rbuf0);
+        // (s = -1: the caller's positions, wrapped into the box by ap_load_kernel, are in Rbuf1)
+        const float2* Rcur  = (s & 1) ? a.Rbuf1 : a.Rbuf0;
         float2*       Rnext = ((s + 1) & 1) ? a.Rbuf1 : a.Rbuf0;
         const int  par     = (int)((s + 1) & 1);
         const bool kick1   = (s >= 0);                     // prologue only evaluates F(R_in)
@@ -393,7 +395,7 @@ ap_persistent_kernel(const ApArgs a) {
             else         ap_phase_forces<IPT, CUTOFF, false>(a, Rcur, sj, sred, par);
         }
         if (prof) { long long t = clock64(); pt[0] += t - pt[4]; pt[4] = t; }
-        grid_barrier(a.bar, (++epoch) * (unsigned)a.G, a.err);
+        grid_barrier(a.bar, (++epoch) * (unsigned)a.G, a.err, a.spin_limit);
         if (prof) { long long t = clock64(); pt[1] += t - pt[4]; pt[4] = t; }
         // cross-GPU epochs of this step (tile mode on several GPUs uses two: partial forces, positions)
         const unsigned xper = (V3 && a.P > 1) ? 2u : 1u;
@@ -411,7 +413,7 @@ ap_persistent_kernel(const ApArgs a) {
                 for (int q = 0; q < a.P; ++q) {
                     if (q == a.rank) continue;
                     while ((int)(mine[q] - xe) < 0) {
-                        if (clock64() - t0 > (1ll << 33)) { atomicExch(a.err, 2); break; }
+                        if (a.spin_limit > 0 && clock64() - t0 > 2 * a.spin_limit) { atomicExch(a.err, 2); break; }
                     }
                 }
                 __threadfence_system();
@@ -449,7 +451,7 @@ ap_persistent_kernel(const ApArgs a) {
                     }
                 }
                 __threadfence_system();
-                grid_barrier(a.bar, (++epoch) * (unsigned)a.G, a.err);
+                grid_barrier(a.bar, (++epoch) * (unsigned)a.G, a.err, a.spin_limit);
                 peer_wait(xe0 + 1u);
             }
         }
@@ -547,12 +549,12 @@ ap_persistent_kernel(const ApArgs a) {
         }
         if (thermo) {
             // velocity rescale: V *= sqrt(kT_target / (KE/N)), KE = 0.5*sum|V|^2
-            grid_barrier(a.bar, (++epoch) * (unsigned)a.G, a.err);
+            grid_barrier(a.bar, (++epoch) * (unsigned)a.G, a.err, a.spin_limit);
             if (tid < 32) {
                 double ke2 = warp_sum_array(a.ke_part + par * a.G, a.G);
                 if (tid == 0) {
                     float ke = (float)(0.5 * ke2);
-                    s_lambda = sqrtf(rc.thermo_kT / (ke / (float)a.N));   // (single-GPU only)
+                    s_lambda = ke > 0.0f ? sqrtf(rc.thermo_kT / (ke / (float)a.N)) : 1.0f;   // (single-GPU only)
                 }
             }
             __syncthreads();
@@ -576,7 +578,7 @@ ap_persistent_kernel(const ApArgs a) {
             }
         }
         if (prof) { long long t = clock64(); pt[2] += t - pt[4]; pt[4] = t; }
-        grid_barrier(a.bar, (++epoch) * (unsigned)a.G, a.err);
+        grid_barrier(a.bar, (++epoch) * (unsigned)a.G, a.err, a.spin_limit);
         if (a.P > 1 && !final) {
             // every rank has pushed its slab into our next-position buffer: one NVLink round trip per step,
             // no NCCL on the step path
@@ -724,7 +726,8 @@ ap_cluster_kernel(const CluArgs a) {
     {
         const float2* Rsrc = (a.s_begin < 0) ? a.R_in : ((a.s_begin & 1) ? a.Rbuf1 : a.Rbuf0);
         for (int j = tid; j < a.N; j += CLU_THREADS) {
-            const float2 r = Rsrc[j];
+            float2 r = Rsrc[j];
+            if (a.s_begin < 0) r = load_wrap(r, pc.box);
             spos[j] = make_float4(-r.x, -r.x, -r.y, -r.y);
         }
     }
@@ -797,7 +800,7 @@ ap_cluster_kernel(const CluArgs a) {
                 double ke2 = 0.0;
                 for (int q = 0; q < a.C; ++q) ke2 += (double)sK[q];
                 const float ke = (float)(0.5 * ke2);
-                s_lambda = sqrtf(rc.thermo_kT / (ke / (float)a.N));
+                s_lambda = ke > 0.0f ? sqrtf(rc.thermo_kT / (ke / (float)a.N)) : 1.0f;
             }
             __syncthreads();
             const float lam = s_lambda;
@@ -852,6 +855,12 @@ ap_cluster_kernel(const CluArgs a) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) a.prof[k * 4 + q] = pt[q];
     }
+}
+
+// the caller's positions -> Rbuf1 (the buffer step s = -1 reads), wrapped into [0, box] (ljmd.h)
+__global__ void ap_load_kernel(const float2* __restrict__ R_in, float2* __restrict__ dst, int N, float box) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) dst[i] = load_wrap(R_in[i], box);
 }
 
 using CluKernel = void (*)(const CluArgs);
@@ -1186,8 +1195,10 @@ int ap_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_out
         if (rc.traj && rc.S > 0)
             LJ_CUDA(cudaMemsetAsync(rc.traj, 0, sizeof(float2) * N * rc.S, st));   // MD:89
     }
+    LJ_CUDA(cudaMemsetAsync(ap->err, 0, sizeof(int), st));     // status of THIS call (ljmd_check)
     ApArgs a{};
     a.pc = h->pc;
+    a.spin_limit = h->spin_limit;
     a.ppc = (ap->Nloc + ap->G - 1) / ap->G;
     a.i_lo = ap->i_lo; a.Nloc = ap->Nloc; a.rank = h->rank; a.P = std::max(1, h->nranks);
     for (int q = 0; q < LJMD_MAX_RANKS; ++q) { a.peerR0[q] = ap->peerR0[q]; a.peerR1[q] = ap->peerR1[q]; a.peer_flags[q] = ap->peer_flags[q]; a.peerF[q] = ap->peerF[q]; }
@@ -1249,6 +1260,9 @@ int ap_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_out
         }
         return 0;
     }
+    ap_load_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(R_in, ap->Rbuf1, (int)N, h->pc.box);
+    LJ_CUDA(cudaGetLastError());
+    h->launches++;
     while (s < s_last) {
         const long long e = std::min(s_last, s + chunk);
         a.s_begin = s; a.s_end = e;
@@ -1305,8 +1319,9 @@ int ap_check_error(ljmd_handle* h) {
     int e = 0;
     LJ_CUDA(cudaMemcpy(&e, ap->err, sizeof(int), cudaMemcpyDeviceToHost));
     if (e) {
-        set_error("all-pairs persistent kernel: grid barrier timed out (device error flag %d)", e);
-        return LJMD_E_STATE;
+        set_error("all-pairs persistent kernel: %s timed out (LJMD_SPIN_TIMEOUT_S)",
+                  e == 2 ? "a peer GPU's arrival word" : "a grid barrier");
+        return LJMD_E_TIMEOUT;
     }
     return 0;
 }

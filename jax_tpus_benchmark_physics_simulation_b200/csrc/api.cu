@@ -3,6 +3,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -66,6 +67,11 @@ int create_common(ljmd_t** out, const ljmd_params* p, int rank, int nranks, cons
     h->rank = rank;
     h->nranks = nranks;
     h->timed = true;
+    {   // device-side spin waits (grid barrier, cross-GPU arrival words) give up after this long
+        double sec = 4.0;
+        if (const char* e = getenv("LJMD_SPIN_TIMEOUT_S")) sec = atof(e);
+        h->spin_limit = sec > 0.0 ? (long long)(sec * 1.0e3 * (double)prop.clockRate) : 0;
+    }
     int path = p->path;
     if (path == LJMD_PATH_AUTO) path = (p->N <= 131072 || !h->pc.cutoff) ? LJMD_PATH_ALLPAIRS : LJMD_PATH_CELLS;
     if (path == LJMD_PATH_CELLS && !h->pc.cutoff) {
@@ -203,13 +209,20 @@ int ljmd_last_rebuilds(ljmd_t* h, int64_t* rebuilds) {
     return 0;
 }
 
+int ljmd_check(ljmd_t* h) {
+    if (!h) { set_error("null handle"); return LJMD_E_INVALID; }
+    LJ_CUDA(cudaSetDevice(h->p.device));
+    LJ_CUDA(cudaStreamSynchronize(h->stream));
+    int e = ap_check_error(h);
+    return e ? e : cells_check_error(h);
+}
+
 int ljmd_last_run_ms(ljmd_t* h, float* ms) {
     if (!h || !ms) { set_error("null argument"); return LJMD_E_INVALID; }
     LJ_CUDA(cudaSetDevice(h->p.device));
     LJ_CUDA(cudaEventSynchronize(h->ev1));
     LJ_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
-    int e = ap_check_error(h);
-    return e ? e : cells_check_error(h);
+    return ljmd_check(h);
 }
 
 int ljmd_allpairs_mode(ljmd_t* h, int32_t* mode) {

@@ -68,8 +68,10 @@ constexpr int CL_WARPS     = CL_THREADS / 32;
 constexpr int CL_ORDER_MAX = 64;    // cells denser than this keep arrival order (see B5)
 
 enum { ST_PR = 0, ST_PV = 1, ST_REBUILDS = 2, ST_ERR = 3, ST_FLAG = 4, ST_NHELD = 5, ST_OWN_S = 6,
-       ST_OWN_E = 7, ST_LOADCNT = 8, ST_XEPOCH = 9, ST_LMOVED = 10, ST_WORDS = 12 };
-enum { CERR_BARRIER = 1, CERR_LIST_OVERFLOW = 2, CERR_PEER = 4, CERR_CAPACITY = 8 };
+       ST_OWN_E = 7, ST_LOADCNT = 8, ST_XEPOCH = 9, ST_LMOVED = 10, ST_ABORT = 11, ST_WORDS = 16 };
+// ST_ERR: conditions that void the RESULT (the kernel itself keeps running in lockstep);
+// ST_ABORT: a spin wait gave up (1 = grid barrier, 2 = peer GPU) - later waits fall through
+enum { CERR_LIST_OVERFLOW = 2, CERR_CAPACITY = 8 };
 // mailbox words a neighbour writes (slab decomposition)
 enum { MB_HI_START = 0, MB_WORDS = 8 };
 
@@ -108,6 +110,7 @@ struct CellsArgs {
     const float2* R_in;
     const float2* V_in;
     long long s_begin, s_end;
+    long long spin_limit;           // clocks a spin wait may last (0 = unlimited)
     RunCtl rc;
     float2 *R_out, *V_out, *F_out;
     float*  pe_out;
@@ -225,7 +228,9 @@ __device__ __forceinline__ bool peer_sync(const CellsArgs& a, Ctx& ctx, bool pay
             if (q == a.me) continue;
             unsigned w;
             while (((w = mine[q]) >> 1) != xe) {
-                if (clock64() - t0 > (1ll << 33)) { atomicOr(a.state + ST_ERR, CERR_PEER); w = 0u; break; }
+                if ((a.spin_limit > 0 && clock64() - t0 > 2 * a.spin_limit) || __ldcg(a.state + ST_ABORT) != 0) {
+                    atomicExch(a.state + ST_ABORT, 2); w = 0u; break;
+                }
             }
             any |= (int)(w & 1u);
         }
@@ -247,7 +252,7 @@ __device__ __forceinline__ bool peer_sync(const CellsArgs& a, Ctx& ctx, bool pay
         }                                                                   \
     } while (0)
 
-#define CL_BARRIER() grid_barrier(a.bar, (++ctx.epoch) * (unsigned)a.G, a.state + ST_ERR)
+#define CL_BARRIER() grid_barrier(a.bar, (++ctx.epoch) * (unsigned)a.G, a.state + ST_ABORT, a.spin_limit)
 
 // ---- rebuild: counting sort by cell, deterministic in-cell order, bitmask Verlet list --------------
 // lim2: list radius squared (rc + skin for a run, the caller's radius in count mode)
@@ -901,7 +906,7 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
         }
         // per-unit energy partials (fixed shuffle tree), summed in unit order after the barrier
         if (PE) {
-            const float t = warp_sum(pe);
+            const float t = warp_sum(live ? pe : 0.0f);       // (idle lanes of a boundary unit evaluate a dummy)
             if (lane == 0) __stcg(&a.pe_part[fl.par * a.nchunks + (u - u_lo)], t);
         }
         if (fl.want_ke) {
@@ -947,14 +952,14 @@ cells_persistent_kernel(const CellsArgs a) {
         // orders them); the halo rows are filled by the neighbours during the rebuild.
         if (a.P == 1) {
             for (int i = gtid; i < a.N; i += gsz) {
-                a.R[ctx.pr][i] = a.R_in[i];
+                a.R[ctx.pr][i] = load_wrap(a.R_in[i], a.pc.box);
                 a.V[ctx.pv][i] = a.V_in ? a.V_in[i] : make_float2(0.0f, 0.0f);
                 a.orig[ctx.pv][i] = i;
             }
             ctx.nheld = a.N;
         } else {
             for (int i = gtid; i < a.N; i += gsz) {
-                const float2 r = a.R_in[i];
+                const float2 r = load_wrap(a.R_in[i], a.pc.box);
                 if (owned_row(a, local_row(a, r.y))) {
                     const int k = atomicAdd(a.state + ST_LOADCNT, 1);
                     if (k < a.Nalloc) {
@@ -1010,7 +1015,7 @@ cells_persistent_kernel(const CellsArgs a) {
         if (thermo) {
             CL_BARRIER();
             const double ke2 = block_sum_array(a.ke_part + par * a.nchunks, u_hi - u_lo, sdbl);
-            if (tid == 0) s_lambda = sqrtf(rc.thermo_kT / ((float)(0.5 * ke2) / (float)a.N));
+            if (tid == 0) s_lambda = ke2 > 0.0 ? sqrtf(rc.thermo_kT / ((float)(0.5 * ke2) / (float)a.N)) : 1.0f;
             __syncthreads();
             const float lam = s_lambda;
             for (int i = ctx.own_s + gtid; i < ctx.own_e; i += gsz) {
@@ -1247,6 +1252,7 @@ static void fill_args(ljmd_handle* h, CellsArgs& a) {
     a.static_frac = 0.6f;      // measured at N = 4M: 0.0 -> 170.3, 0.5 -> 160.4, 0.7 -> 161.4, 0.9 -> 171.0, 1.0 -> 174.7 us/step
     if (const char* e = getenv("LJMD_CELLS_STATIC")) a.static_frac = fminf(1.0f, fmaxf(0.0f, (float)atof(e)));
     a.dt = h->p.dt;
+    a.spin_limit = h->spin_limit;
     for (int q = 0; q < cl->P; ++q) {
         char* base = cl->peer_base[q];
         for (int k = 0; k < 2; ++k) {
@@ -1302,10 +1308,9 @@ int cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_
     }
     if (rc.nsteps > 0 && rc.traj && rc.S > 0)
         LJ_CUDA(cudaMemsetAsync(rc.traj, 0, sizeof(float2) * N * rc.S, st));      // MD:89
-    // fresh call: parities 0, rebuild counter 0, flags 0 (the error word and the cross-GPU epoch persist)
-    LJ_CUDA(cudaMemsetAsync(cl->state, 0, sizeof(int) * 3, st));
-    LJ_CUDA(cudaMemsetAsync(cl->state + ST_FLAG, 0, sizeof(int) * (ST_XEPOCH - ST_FLAG), st));
-    LJ_CUDA(cudaMemsetAsync(cl->state + ST_LMOVED, 0, sizeof(int), st));
+    // fresh call: parities 0, rebuild counter 0, flags and status words 0 (the cross-GPU epoch persists)
+    LJ_CUDA(cudaMemsetAsync(cl->state, 0, sizeof(int) * ST_XEPOCH, st));
+    LJ_CUDA(cudaMemsetAsync(cl->state + ST_LMOVED, 0, sizeof(int) * (ST_WORDS - ST_LMOVED), st));
     CellsArgs a{};
     fill_args(h, a);
     a.R_in = R_in; a.V_in = V_in;
@@ -1388,8 +1393,8 @@ int cells_neighbor_count(ljmd_handle* h, const float2* R, float radius, int* nbr
         return LJMD_E_INVALID;
     }
     if (cl->P > 1) { set_error("neighbor_count is single-GPU only"); return LJMD_E_UNSUPPORTED; }
-    LJ_CUDA(cudaMemsetAsync(cl->state, 0, sizeof(int) * 3, h->stream));
-    LJ_CUDA(cudaMemsetAsync(cl->state + ST_FLAG, 0, sizeof(int) * (ST_XEPOCH - ST_FLAG), h->stream));
+    LJ_CUDA(cudaMemsetAsync(cl->state, 0, sizeof(int) * ST_XEPOCH, h->stream));
+    LJ_CUDA(cudaMemsetAsync(cl->state + ST_LMOVED, 0, sizeof(int) * (ST_WORDS - ST_LMOVED), h->stream));
     CellsArgs a{};
     fill_args(h, a);
     a.R_in = R; a.V_in = nullptr;
@@ -1411,15 +1416,23 @@ long long cells_last_rebuilds(ljmd_handle* h) {
 int cells_check_error(ljmd_handle* h) {
     Cells* cl = h->cells;
     if (!cl) return 0;
-    int e = 0;
-    LJ_CUDA(cudaMemcpy(&e, cl->state + ST_ERR, sizeof(int), cudaMemcpyDeviceToHost));
-    if (e & CERR_LIST_OVERFLOW) {
-        set_error("cell-list: a particle needs more than %d list entries (too dense for rc+skin)", CL_E);
-        return LJMD_E_STATE;
+    int e[ST_WORDS] = {};
+    LJ_CUDA(cudaMemcpy(e, cl->state, sizeof(e), cudaMemcpyDeviceToHost));
+    if (e[ST_ABORT]) {
+        set_error("cell-list persistent kernel: %s timed out (LJMD_SPIN_TIMEOUT_S)",
+                  e[ST_ABORT] == 2 ? "a peer GPU's arrival word" : "a grid barrier");
+        return LJMD_E_TIMEOUT;
     }
-    if (e & CERR_CAPACITY) { set_error("cell-list: a slab holds more particles than its buffers (density too uneven)"); return LJMD_E_STATE; }
-    if (e & CERR_PEER) { set_error("cell-list: a peer GPU did not arrive at a cross-GPU synchronisation"); return LJMD_E_STATE; }
-    if (e) { set_error("cell-list persistent kernel: grid barrier timed out (flag %d)", e); return LJMD_E_STATE; }
+    if (e[ST_ERR] & CERR_LIST_OVERFLOW) {
+        set_error("cell-list: a particle has more neighbours within rc + skin than its Verlet list holds "
+                  "(%d; %d (slot, mask) entries for warps at the box edge): too dense for this rc + skin",
+                  4 * CL_NW, CL_E);
+        return LJMD_E_OVERFLOW;
+    }
+    if (e[ST_ERR] & CERR_CAPACITY) {
+        set_error("cell-list: a slab holds more particles than its buffers (density too uneven over the GPUs)");
+        return LJMD_E_OVERFLOW;
+    }
     return 0;
 }
 

@@ -12,39 +12,38 @@
 #include "ljmd_internal.cuh"
 
 #include <dlfcn.h>
+#include <nccl.h>
 #include <cstring>
 
 namespace ljmd {
 
 namespace {
 
-typedef struct ncclComm* ncclComm_t;
-typedef struct { char internal[128]; } ncclUniqueId;
-enum { ncclFloat32 = 7, ncclInt8 = 0, ncclSum = 0 };
-
+// types and enum values come from the NCCL header; the functions are resolved at run time
 struct Nccl {
     void* lib = nullptr;
-    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
-    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-    int (*CommDestroy)(ncclComm_t) = nullptr;
-    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
-    const char* (*GetErrorString)(int) = nullptr;
+    decltype(&ncclGetUniqueId)    GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank)   CommInitRank = nullptr;
+    decltype(&ncclCommDestroy)    CommDestroy = nullptr;
+    decltype(&ncclAllGather)      AllGather = nullptr;
+    decltype(&ncclAllReduce)      AllReduce = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
 };
 
-Nccl g_nccl;
+Nccl g_nccl;     // published only when every symbol has been resolved
 
 int load_nccl() {
     if (g_nccl.lib) return 0;
+    Nccl n;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char* n : names) {
-        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
-        if (g_nccl.lib) break;
+    for (const char* nm : names) {
+        n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (n.lib) break;
     }
-    if (!g_nccl.lib) { set_error("cannot dlopen libnccl.so.2: %s", dlerror()); return LJMD_E_NCCL; }
+    if (!n.lib) { set_error("cannot dlopen libnccl.so.2: %s", dlerror()); return LJMD_E_NCCL; }
 #define LJ_SYM(field, name)                                                        \
-    *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, name);                            \
-    if (!g_nccl.field) { set_error("libnccl lacks %s", name); return LJMD_E_NCCL; }
+    *(void**)(&n.field) = dlsym(n.lib, name);                                      \
+    if (!n.field) { set_error("libnccl lacks %s", name); dlclose(n.lib); return LJMD_E_NCCL; }
     LJ_SYM(GetUniqueId, "ncclGetUniqueId")
     LJ_SYM(CommInitRank, "ncclCommInitRank")
     LJ_SYM(CommDestroy, "ncclCommDestroy")
@@ -52,6 +51,7 @@ int load_nccl() {
     LJ_SYM(AllReduce, "ncclAllReduce")
     LJ_SYM(GetErrorString, "ncclGetErrorString")
 #undef LJ_SYM
+    g_nccl = n;
     return 0;
 }
 
@@ -59,7 +59,7 @@ int load_nccl() {
     do {                                                                           \
         int _r = (expr);                                                           \
         if (_r != 0) {                                                             \
-            set_error("%s failed: %s", #expr, g_nccl.GetErrorString(_r));          \
+            set_error("%s failed: %s", #expr, g_nccl.GetErrorString((ncclResult_t)_r)); \
             return LJMD_E_NCCL;                                                    \
         }                                                                          \
     } while (0)
@@ -78,6 +78,7 @@ int dist_init(ljmd_handle* h, const void* nccl_unique_id) {
     if (r) return r;
     Dist* d = new Dist();
     h->dist = d;
+    static_assert(sizeof(ncclUniqueId) == 128, "ljmd.h promises a 128-byte unique id");
     ncclUniqueId id;
     memcpy(&id, nccl_unique_id, sizeof(id));
     LJ_NCCL(g_nccl.CommInitRank(&d->comm, h->nranks, id, h->rank));
@@ -115,18 +116,24 @@ int dist_share(ljmd_handle* h, void* local_base, void** peer_bases) {
     if (!d) { set_error("dist_share without a communicator"); return LJMD_E_STATE; }
     cudaIpcMemHandle_t mine;
     LJ_CUDA(cudaIpcGetMemHandle(&mine, local_base));
-    char* dev = nullptr;
     const size_t hs = sizeof(cudaIpcMemHandle_t);
-    LJ_CUDA(cudaMalloc(&dev, hs * h->nranks));
-    LJ_CUDA(cudaMemcpy(dev + hs * h->rank, &mine, hs, cudaMemcpyHostToDevice));
-    LJ_NCCL(g_nccl.AllGather(dev + hs * h->rank, dev, hs, ncclInt8, d->comm, h->stream));
-    LJ_CUDA(cudaStreamSynchronize(h->stream));
     cudaIpcMemHandle_t all[LJMD_MAX_RANKS];
-    LJ_CUDA(cudaMemcpy(all, dev, hs * h->nranks, cudaMemcpyDeviceToHost));
-    LJ_CUDA(cudaFree(dev));
+    char* dev = nullptr;
+    LJ_CUDA(cudaMalloc(&dev, hs * h->nranks));
+    auto exchange = [&]() -> int {          // (dev is released on every path below)
+        LJ_CUDA(cudaMemcpy(dev + hs * h->rank, &mine, hs, cudaMemcpyHostToDevice));
+        LJ_NCCL(g_nccl.AllGather(dev + hs * h->rank, dev, hs, ncclInt8, d->comm, h->stream));
+        LJ_CUDA(cudaStreamSynchronize(h->stream));
+        LJ_CUDA(cudaMemcpy(all, dev, hs * h->nranks, cudaMemcpyDeviceToHost));
+        return 0;
+    };
+    const int r = exchange();
+    cudaFree(dev);
+    if (r) return r;
     for (int q = 0; q < h->nranks; ++q) {
         if (q == h->rank) { peer_bases[q] = local_base; continue; }
         void* pq = nullptr;
+        // (mappings opened so far are recorded in d->peer_mapped and closed by dist_destroy)
         LJ_CUDA(cudaIpcOpenMemHandle(&pq, all[q], cudaIpcMemLazyEnablePeerAccess));
         peer_bases[q] = pq;
         d->peer_mapped[q] = pq;

@@ -203,21 +203,31 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 
 // Grid-wide barrier for a cooperative (co-resident) launch: monotone arrival counter in L2.
 // `target` = number of arrivals that completes this barrier (epoch * gridDim.x).
-// A spin that lasts longer than ~2^32 clocks (about 2 s) raises *err and falls through, so a
-// lost rank can never hang the GPU.
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target, int* err) {
+// A spin that lasts longer than `limit` clocks (LJMD_SPIN_TIMEOUT_S; 0 = never) raises *abort_flag and
+// falls through, so a lost rank can never hang the GPU.  *abort_flag holds ONLY such aborts (the
+// list / capacity flags live in another word): once it is set the run is void and later barriers fall
+// through at once.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target, int* abort_flag,
+                                             long long limit) {
     __syncthreads();                       // every thread's writes are ordered before thread 0's release
     if (threadIdx.x == 0) {
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-        long long t0 = clock64();
-        // once a barrier has timed out the run is void: later barriers fall through at once
-        if (__ldcg(err) == 0) {
+        if (__ldcg(abort_flag) == 0) {
+            const long long t0 = clock64();
             while (ld_acquire_gpu(counter) < target) {
-                if (clock64() - t0 > (1ll << 32)) { atomicExch(err, 1); break; }
+                if (limit > 0 && clock64() - t0 > limit) { atomicExch(abort_flag, 1); break; }
             }
         }
     }
     __syncthreads();                       // ... and the acquire is ordered before every thread's reads
+}
+
+// A caller's position on its way into the library: coordinates inside the closed interval [0, box]
+// (all a step can produce, MD:72) pass bit for bit, anything else is wrapped like jnp.mod.
+__device__ __forceinline__ float2 load_wrap(float2 r, float box) {
+    if (!(r.x >= 0.0f && r.x <= box)) r.x = wrap_box(r.x, box);
+    if (!(r.y >= 0.0f && r.y <= box)) r.y = wrap_box(r.y, box);
+    return r;
 }
 
 }  // namespace ljmd

@@ -77,6 +77,7 @@ struct ljmd_handle {
     bool             timed;
     long long        launches;
     int              rank, nranks;
+    long long        spin_limit;  // clocks a device-side spin wait may last (0 = unlimited)
 };
 
 namespace ljmd {

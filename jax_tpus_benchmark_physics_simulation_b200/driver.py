@@ -5,8 +5,10 @@
 Same flags and defaults as molecular_dynamics_jax_single-host_workload.py (MD:196-213) and the
 same three dispatch/sync points (MD:142-145, 151-152, 162-163).  Additions (all default to the
 reference's behaviour): ``--rc`` (cutoff, default none), ``--path`` (auto|allpairs|cells),
-``--ic`` (lattice|uniform; the reference's uniform placement overflows fp32 by step 2 —
-SURVEY.md §0 — so ``lattice`` is the default), ``--energy_every``.  matplotlib is imported
+``--ic`` (uniform|lattice; ``uniform`` = the reference's own placement, MD:133-135, and therefore
+the default: like the reference's run it overflows fp32 within a few steps - SURVEY.md §0 - and
+finishes with non-finite positions; ``lattice`` is the physical lattice+jitter state that the
+parity tests and bench.py use), ``--energy_every``.  matplotlib is imported
 lazily (absent in this image): without it g(r) is written as ``.npy``/``.csv`` next to
 ``--output``.
 """
@@ -110,7 +112,9 @@ def build_parser():
     # additions (defaults reproduce the reference)
     parser.add_argument("--rc", type=float, default=None, help="cutoff radius (default: none, as the reference)")
     parser.add_argument("--path", choices=["auto", "allpairs", "cells"], default="auto")
-    parser.add_argument("--ic", choices=["lattice", "uniform"], default="lattice")
+    parser.add_argument("--ic", choices=["uniform", "lattice"], default="uniform",
+                        help="initial positions: uniform = the reference's (MD:133-135, default); "
+                             "lattice = square lattice + 5%% jitter (physical)")
     parser.add_argument("--energy_every", type=int, default=0)
     return parser
 

@@ -31,13 +31,19 @@ class DeviceArray:
     """Minimal jax.Array look-alike over a CUDA torch tensor: ``.block_until_ready()``
     (MD:145,152,163), ``.shape`` (MD:174), ``__array__`` for numpy/matplotlib (MD:181)."""
 
-    __slots__ = ("tensor",)
+    __slots__ = ("tensor", "_check")
 
-    def __init__(self, tensor: torch.Tensor):
+    def __init__(self, tensor: torch.Tensor, check=None):
         self.tensor = tensor
+        # status hook of the simulation that produced the array: the kernels run asynchronously, so
+        # device-side failures (Verlet-list / slab overflow, barrier timeout) can only be raised
+        # where the caller synchronises - exactly where the reference blocks (MD:145,152,163)
+        self._check = check
 
     def block_until_ready(self) -> "DeviceArray":
         torch.cuda.current_stream(self.tensor.device).synchronize()
+        if self._check is not None:
+            self._check()
         return self
 
     @property
@@ -52,9 +58,11 @@ class DeviceArray:
         return self.tensor.shape[0]
 
     def __getitem__(self, idx):
-        return DeviceArray(self.tensor[idx])
+        return DeviceArray(self.tensor[idx], self._check)
 
     def __array__(self, dtype=None, copy=None):
+        if self._check is not None:
+            self._check()
         a = self.tensor.detach().cpu().numpy()
         return a.astype(dtype) if dtype is not None else a
 
@@ -62,6 +70,8 @@ class DeviceArray:
         return self.__array__()
 
     def __float__(self):
+        if self._check is not None:
+            self._check()
         return float(self.tensor.item())
 
     def __repr__(self):
@@ -134,6 +144,16 @@ class LJSimulation:
         except Exception:
             pass
 
+    def check(self) -> None:
+        """Block until the handle's stream is idle and raise :class:`LjmdError` if the last call
+        flagged a device-side failure (ljmd_check, include/ljmd.h)."""
+        if getattr(self, "_h", None) is None or not self._h.value:
+            return                      # handle already destroyed: nothing left to ask
+        _lib.check(self.lib.ljmd_check(self._h), "ljmd_check")
+
+    def _arr(self, t: torch.Tensor) -> DeviceArray:
+        return DeviceArray(t, self.check)
+
     def _dev(self, x, shape: Optional[Sequence[int]] = None) -> torch.Tensor:
         """Accept DeviceArray / torch (cpu or cuda) / numpy; return contiguous fp32 CUDA tensor."""
         if isinstance(x, DeviceArray):
@@ -176,7 +196,7 @@ class LJSimulation:
         self._check_stream()
         _lib.check(self.lib.ljmd_energy(self._h, R.data_ptr(), out.data_ptr()), "ljmd_energy")
         self._after()
-        return DeviceArray(out[0])
+        return self._arr(out[0])
 
     # ------------------------------------------------------------------ MD:64
     def force_fn(self, R) -> DeviceArray:
@@ -185,7 +205,7 @@ class LJSimulation:
         self._check_stream()
         _lib.check(self.lib.ljmd_forces(self._h, R.data_ptr(), F.data_ptr(), None), "ljmd_forces")
         self._after()
-        return DeviceArray(F)
+        return self._arr(F)
 
     def force_and_energy(self, R) -> Tuple[DeviceArray, DeviceArray]:
         R = self._dev(R, (self.N, 2))
@@ -195,7 +215,7 @@ class LJSimulation:
         _lib.check(self.lib.ljmd_forces(self._h, R.data_ptr(), F.data_ptr(), pe.data_ptr()),
                    "ljmd_forces")
         self._after()
-        return DeviceArray(F), DeviceArray(pe[0])
+        return self._arr(F), self._arr(pe[0])
 
     # ------------------------------------------------------------------ MD:66-106
     def _run(self, state, nsteps: int, sample_every: int = 0, energy_every: int = 0):
@@ -215,8 +235,8 @@ class LJSimulation:
             energy_every if ne else 0, ke_pe.data_ptr() if ne else None,
             self.thermostat_kT, self.thermostat_every), "ljmd_run")
         self._after()
-        self.last_energies = DeviceArray(ke_pe) if ne else None
-        return (DeviceArray(R_out), DeviceArray(V_out)), DeviceArray(traj)
+        self.last_energies = self._arr(ke_pe) if ne else None
+        return (self._arr(R_out), self._arr(V_out)), self._arr(traj)
 
     def verlet_step(self, state):
         """One velocity-Verlet step (MD:66-75)."""

@@ -17,7 +17,7 @@ def test_driver_default_flags_small(tmp_path):
     out = str(tmp_path / "g_r_plot.png")
     args = driver.build_parser().parse_args(
         ["--N", "400", "--eq_steps", "300", "--prod_steps", "300", "--sample_every", "100",
-         "--output", out, "--energy_every", "100"])
+         "--output", out, "--energy_every", "100", "--ic", "lattice"])
     assert args.rho == 0.8 and args.kT == 1.0 and args.dt == 1e-3 and args.seed == 42   # MD defaults
     state_final, R_history, (r, g) = driver.main(args)
     assert R_history.shape == (3, 400, 2)
@@ -25,6 +25,30 @@ def test_driver_default_flags_small(tmp_path):
     assert os.path.exists(out) or os.path.exists(out.rsplit(".", 1)[0] + ".npy")
     pos = state_final[0].numpy()
     assert np.isfinite(pos).all()
+
+
+def test_driver_reference_uniform_ic_completes(tmp_path):
+    """--ic uniform is the default, as MD:133-135: overlapping particles, fp32 overflow within a
+    few steps.  Like the reference's run it must finish (no hang, no exception) even
+    though the state goes non-finite."""
+    from jax_tpus_benchmark_physics_simulation_b200 import driver
+    out = str(tmp_path / "g_r_plot.png")
+    args = driver.build_parser().parse_args(
+        ["--N", "400", "--eq_steps", "200", "--prod_steps", "200", "--sample_every", "100", "--output", out])
+    assert args.ic == "uniform"
+    state_final, R_history, (r, g) = driver.main(args)
+    assert R_history.shape == (2, 400, 2) and g.shape == r.shape
+    # and on the cell-list path (clumps overflow a Verlet list: reported, not hidden)
+    from jax_tpus_benchmark_physics_simulation_b200 import reference_style_uniform
+    from jax_tpus_benchmark_physics_simulation_b200._lib import LjmdError
+    from jax_tpus_benchmark_physics_simulation_b200.md import LJSimulation
+    R, V, box = reference_style_uniform(16384, seed=42)
+    sim = LJSimulation(16384, rc=2.5, dt=1e-3, path="cells")
+    (R1, _), _ = sim.run((R, V), 20)
+    try:
+        R1.block_until_ready()
+    except LjmdError as e:
+        assert e.code in (-6, -7)
 
 
 def test_reference_defaults_match_parser():

@@ -167,3 +167,38 @@ def test_golden_fixture(oracle):
     R10, V10, _, _ = oracle.c_run(R, V, box, 0.005, 10, rc=2.5)
     assert np.abs(R10 - z["R10_rc25"]).max() < 5e-6
     assert np.abs(V10 - z["V10_rc25"]).max() < 5e-5
+
+
+def test_initial_conditions_reference_style_uniform():
+    """MD:133-135: R ~ U[0,1) * box, V ~ N(0,1) * sqrt(kT) (statistically; threefry bit parity with
+    jax.random is version dependent)."""
+    from jax_tpus_benchmark_physics_simulation_b200 import box_size, reference_style_uniform
+    N, rho, kT = 40000, 0.8, 1.7
+    R, V, box = reference_style_uniform(N, rho, kT, seed=42)
+    assert R.dtype == np.float32 and V.dtype == np.float32 and R.shape == (N, 2) == V.shape
+    assert box == box_size(N, rho) and box.dtype == np.float32
+    assert R.min() >= 0.0 and R.max() < float(box)
+    assert abs(R.mean() / float(box) - 0.5) < 0.01                       # uniform: mean 1/2, var 1/12
+    assert abs(R.var() / float(box) ** 2 - 1.0 / 12.0) < 0.002
+    assert abs(V.mean()) < 0.02 and abs(V.var() / kT - 1.0) < 0.02       # Maxwell: <v^2> = kT per component
+    R2, V2, _ = reference_style_uniform(N, rho, kT, seed=42)
+    assert np.array_equal(R, R2) and np.array_equal(V, V2)               # seeded
+    R3, _, _ = reference_style_uniform(N, rho, kT, seed=43)
+    assert not np.array_equal(R, R3)
+    # nearest pair of the uniform placement is far inside the LJ core (why the run overflows)
+    sub = R[:2000].astype(np.float64)
+    d = sub[:, None, :] - sub[None, :, :]
+    d -= float(box) * np.round(d / float(box))
+    r2 = (d ** 2).sum(-1) + np.eye(len(sub)) * 1e9
+    assert r2.min() < 0.25 ** 2 * (N / 2000)
+
+
+def test_lattice_jitter_shape_and_seed():
+    from jax_tpus_benchmark_physics_simulation_b200 import lattice_jitter
+    R, V, box = lattice_jitter(1024, seed=5)
+    assert R.shape == (1024, 2) and R.min() >= 0.0 and R.max() <= float(box)
+    a = float(box) / 32
+    cell = np.floor(R / a).astype(int)
+    assert len({(int(i), int(j)) for i, j in cell}) == 1024                 # one particle per lattice cell
+    with pytest.raises(ValueError):
+        lattice_jitter(1000)
