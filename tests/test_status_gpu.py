@@ -57,20 +57,21 @@ def test_list_overflow_raises_from_run():
 
 
 def test_status_is_per_call():
+    """The overflow flag belongs to a call, not to the handle: a clumped configuration (all particles
+    squeezed into 16 % of the box: ~120 neighbours within rc + skin) overflows the lists, the regular
+    configuration on the SAME handle then runs clean."""
     from jax_tpus_benchmark_physics_simulation_b200._lib import LjmdError
     N = 16384
-    Rd, Vd, _ = _dense(N, 2.0)
-    sim = _sim(N, rho=2.0, rc=3.5, dt=1e-4, path="cells")
-    sim.run((Rd, Vd), 1)
+    R, V, box = lattice_jitter(N, seed=0)
+    sim = _sim(N, rc=2.5, dt=0.005, path="cells")
+    clumped = (R * np.float32(0.4)).astype(np.float32)
+    Fc = sim.force_fn(clumped)
     with pytest.raises(LjmdError):
-        sim.check()
-    # same handle, a configuration that fits its lists (a sparse grid of particles in the same box)
-    L = float(sim.box_size)
-    sparse = np.empty((N, 2), dtype=np.float32)
-    sparse[:, 0] = np.linspace(0.0, L, N, endpoint=False, dtype=np.float32)
-    sparse[:, 1] = (np.arange(N) % 97) * (L / 97.0)
-    F = sim.force_fn(sparse)
+        Fc.block_until_ready()
+    F = sim.force_fn(R)
     F.block_until_ready()                                       # the flags were cleared when the call started
+    (R1, _), _ = sim.run((R, V), 3)
+    R1.block_until_ready()
 
 
 @pytest.mark.parametrize("path,N", [("allpairs", 400), ("allpairs", 4096), ("cells", 16384)])
