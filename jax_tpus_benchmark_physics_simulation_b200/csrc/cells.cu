@@ -23,13 +23,15 @@
 //   Rb       float2  positions at the last rebuild (max-displacement test against skin/2)
 //   meta     uint32  number of list entries | edge flag << 8 (particle needs the minimum image)
 //   ent      uint2   list entries, ELL layout ent[k * Nalloc + i] = (first slot, mask)
-//   wplan    int4 x2 per warp of 32 slots: the three contiguous slot windows that hold every
-//                    neighbour of the warp's particles.  The per-step pass copies them to shared
-//                    memory with coalesced loads, so the gathers of the pair loop are LDS, not
-//                    scattered global loads.
+//   wplan    int4    per warp of 32 slots ("unit"): the three contiguous slot windows that hold every
+//                    neighbour of the warp's particles (even start, even length: 16-byte granules)
+//                    and the list length.  The per-step pass fetches them with ONE bulk copy each
+//                    (cp.async.bulk -> UBLKCP, completion on an mbarrier), so the gathers of the pair
+//                    loop are LDS, not scattered global loads.
 //   nb4      uint32  for such a warp the list is stored EXPANDED: one byte per neighbour = its index
-//                    in the staged windows (<= 252 slots), four per word, ELL layout, padded with a
-//                    sentinel index to the warp's longest list: decode is a shift, there is no
+//                    in the staged windows (<= 252 slots), four per word, [unit][word][lane] so that a
+//                    unit's words are ONE contiguous block (one more bulk copy), padded with a
+//                    sentinel index to the warp's longest list: decode is a byte extract, there is no
 //                    per-lane trip count.  (first slot, mask) entries remain for the other warps.
 //   cell_start int32 prefix-sum cell index over nrows*nbx cells (+1)
 //
@@ -56,14 +58,19 @@ constexpr int CL_WIN       = 84;    // staged window capacity per stencil row an
 constexpr int CL_WSLOTS    = 256;   // a warp's staging buffer: three windows + 4 sentinel slots
 constexpr int CL_DUMMY     = 255;   // byte index of a sentinel slot (pads the byte lists)
 constexpr int CL_NW        = 24;    // byte-list words per particle (96 neighbours)
-constexpr int CL_NWPRE     = 6;     // words requested before the loop (24 neighbours)
+constexpr int CL_NWS       = 10;    // list words per lane that are staged in shared memory (40 neighbours;
+                                    // longer lists read their tail from global memory)
 constexpr int CL_BROW      = 4 * CL_NW + 4;   // a lane's byte row while a list is built (17 words:
                                               // rows of different lanes start in different banks)
-// per-warp shared memory: two window buffers (the per-step pass double-buffers them with cp.async)
-// and two word buffers (the first CL_NWPRE list words of every lane); the list build uses window
-// buffer 0 and lays its byte rows over the rest
-constexpr int CL_WARP_SMEM = 2 * CL_WSLOTS * 8 + 2 * CL_NWPRE * 32 * 4;  // bytes per warp
-static_assert(CL_WSLOTS * 8 + 32 * CL_BROW <= CL_WARP_SMEM, "byte rows must fit behind window buffer 0");
+// per-warp shared memory: two window buffers and two word buffers (the per-step pass double-buffers
+// them with bulk copies, cp.async.bulk + mbarrier); the list build uses window buffer 0 and lays its
+// byte rows over the rest
+constexpr int CL_WINBYTES  = CL_WSLOTS * 8;                 // 2048
+constexpr int CL_SWBYTES   = CL_NWS * 32 * 4;               // 1280
+constexpr int CL_WARP_SMEM = 2 * CL_WINBYTES + 2 * CL_SWBYTES;   // bytes per warp (6656)
+constexpr int CL_UNITWORDS = CL_NW * 32;                    // list words of one 32-slot unit in nb4
+static_assert(CL_WINBYTES + 32 * CL_BROW <= CL_WARP_SMEM, "byte rows must fit behind window buffer 0");
+static_assert(CL_WARP_SMEM % 16 == 0 && CL_WIN % 2 == 0, "bulk copies need 16-byte granularity");
 constexpr int CL_WARPS     = CL_THREADS / 32;
 constexpr int CL_ORDER_MAX = 64;    // cells denser than this keep arrival order (see B5)
 
@@ -101,8 +108,8 @@ struct CellsArgs {
     int *key, *rank, *tmpk, *tmpo, *tmpc, *cell_count, *cell_start, *row_tot;
     unsigned* meta;
     uint2*    ent;
-    unsigned* nb4;                  // byte lists of staged warps, ELL nb4[w * Nalloc + i]
-    int4*     wplan;                // per warp of 32 slots: 2 x int4 (window starts / lengths, flag)
+    unsigned* nb4;                  // byte lists of staged units, nb4[(unit * CL_NW + w) * 32 + lane]
+    int4*     wplan;                // per unit: (ws0, ws1, ws2, wn0 | wn1 << 8 | wn2 << 16 | nw << 24 | staged << 31)
     float  *pe_part, *ke_part;      // [2*nchunks] per-unit partials (by step parity); nchunks = unit capacity
     int*      sched;                // [2] chunk counters (by step parity)
     int*      state;                // ST_* words
@@ -240,6 +247,8 @@ __device__ __forceinline__ bool peer_sync(const CellsArgs& a, Ctx& ctx, bool pay
     __syncthreads();
     const bool r = s_any != 0;
     __syncthreads();
+    // the peers' halo stores are read by bulk copies (async proxy) from here on
+    asm volatile("fence.proxy.async;" ::: "memory");
     return r;
 }
 
@@ -252,7 +261,14 @@ __device__ __forceinline__ bool peer_sync(const CellsArgs& a, Ctx& ctx, bool pay
         }                                                                   \
     } while (0)
 
-#define CL_BARRIER() grid_barrier(a.bar, (++ctx.epoch) * (unsigned)a.G, a.state + ST_ABORT, a.spin_limit)
+// (the proxy fences order this thread's global stores against the bulk copies other CTAs issue after
+//  the barrier, see fence_proxy_async)
+#define CL_BARRIER()                                                                                  \
+    do {                                                                                              \
+        asm volatile("fence.proxy.async;" ::: "memory");                                              \
+        grid_barrier(a.bar, (++ctx.epoch) * (unsigned)a.G, a.state + ST_ABORT, a.spin_limit);         \
+        asm volatile("fence.proxy.async;" ::: "memory");                                              \
+    } while (0)
 
 // ---- rebuild: counting sort by cell, deterministic in-cell order, bitmask Verlet list --------------
 // lim2: list radius squared (rc + skin for a run, the caller's radius in count mode)
@@ -531,14 +547,15 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
                 }
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    wn[k] -= ws[k];
+                    // 16-byte granules for the bulk copies of the per-step pass: even first slot, even
+                    // length (the extra slots are real slots of the array; the list never names them)
+                    const int e = wn[k];
+                    ws[k] &= ~1;
+                    wn[k] = (e - ws[k] + 1) & ~1;
                     staged = staged && (wn[k] <= CL_WIN);
                 }
             }
-            if (lane == 0) {
-                a.wplan[2 * (i0 >> 5)]     = make_int4(ws[0], ws[1], ws[2], staged ? 1 : 0);
-                a.wplan[2 * (i0 >> 5) + 1] = make_int4(wn[0], wn[1], wn[2], 0);
-            }
+            int plan_w = staged ? (int)(0x80000000u | (unsigned)wn[0] | ((unsigned)wn[1] << 8) | ((unsigned)wn[2] << 16)) : 0;
             int n = 0, cnt = 0;
             if (staged) {
                 // fast path: the warp's windows in shared memory (coalesced copy), every lane scans its
@@ -594,9 +611,10 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
                     for (int q = min(nn, 4 * CL_NW); q < 4 * nwmax; ++q) myb[q] = (unsigned char)CL_DUMMY;
                     if (nw > CL_NW) atomicOr(a.state + ST_ERR, CERR_LIST_OVERFLOW);
                     const unsigned* myw = reinterpret_cast<const unsigned*>(myb);
-                    for (int u = 0; u < nwmax; ++u) a.nb4[(size_t)u * a.Nalloc + i] = myw[u];
+                    unsigned* dst = a.nb4 + (size_t)(i0 >> 5) * CL_UNITWORDS + lane;
+                    for (int u = 0; u < nwmax; ++u) dst[u * 32] = myw[u];
                 }
-                if (lane == 0) a.wplan[2 * (i0 >> 5) + 1].w = nwmax;
+                plan_w |= nwmax << 24;
                 n = 0;
             } else if (live) {
                 const int lo = b - CL_K, hi = b + CL_K;
@@ -633,6 +651,7 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
                     }
                 }
             }
+            if (lane == 0) a.wplan[i0 >> 5] = make_int4(ws[0], ws[1], ws[2], plan_w);
             if (!live) continue;
             if (a.mode == 0) {
                 if (n > CL_E) atomicOr(a.state + ST_ERR, CERR_LIST_OVERFLOW);
@@ -716,47 +735,83 @@ __device__ __forceinline__ void list_force(const CellsArgs& a, const float2* R, 
     if (PE) pe = pe2.x + pe2.y;
 }
 
-// staged warps: the list is one byte per neighbour (index into the staged windows), four per word,
-// padded with the sentinel index to the warp's longest list (nw words, warp-uniform)
+// ---- bulk copies (cp.async.bulk = UBLKCP, the 1-D TMA path) completing on an mbarrier ---------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// generic-proxy writes (st.global of the integrate epilogue / the rebuild) must be ordered against the
+// async-proxy reads of later bulk copies: one proxy fence on each side of every grid barrier
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ float2 lds64(unsigned addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned lds32(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// staged units: the list is one byte per neighbour (index into the staged windows), four per word,
+// padded with the sentinel index to the warp's longest list (nw words, warp-uniform).  `win` is the
+// 32-bit shared-memory address of the staged windows: byte extract + scaled add + LDS.64 per neighbour.
 template <bool PE>
-__device__ __forceinline__ void word_eval(const PairConsts& pc, const PairConsts2& c2, const float2* win,
+__device__ __forceinline__ void word_eval(const PairConsts& pc, const PairConsts2& c2, unsigned win,
                                           unsigned word, float2 nri, float2& acc, float2& pe2) {
-    const float2 r0 = win[word & 0xffu], r1 = win[(word >> 8) & 0xffu];
-    const float2 r2 = win[(word >> 16) & 0xffu], r3 = win[word >> 24];
+    const float2 r0 = lds64(win + (__byte_perm(word, 0u, 0x4440u) << 3));
+    const float2 r1 = lds64(win + (__byte_perm(word, 0u, 0x4441u) << 3));
+    const float2 r2 = lds64(win + (__byte_perm(word, 0u, 0x4442u) << 3));
+    const float2 r3 = lds64(win + (__byte_perm(word, 0u, 0x4443u) << 3));
     eval_two<PE, false>(pc, c2, nri, r0, r1, true, acc, pe2);
     eval_two<PE, false>(pc, c2, nri, r2, r3, true, acc, pe2);
 }
 
-// ---- cp.async (LDGSTS) helpers: global -> shared without passing through registers ------------------
-__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// staged units: the list is one byte per neighbour (index into the staged windows), four per word,
-// padded with the sentinel index to the warp's longest list (nw words, warp-uniform); the first
-// CL_NWPRE words of every lane were copied to shared memory together with the windows
+// all listed neighbours of one particle of a staged unit: the first CL_NWS words of every lane arrived
+// in shared memory with the windows, longer lists continue from global memory
 template <bool PE>
-__device__ __forceinline__ void bytes_force_staged(const CellsArgs& a, const float2* win, const unsigned* sw,
-                                                   int i, int nw, float2 ri, float& Fx, float& Fy, float& pe) {
+__device__ __forceinline__ void bytes_force_staged(const CellsArgs& a, unsigned win, unsigned sw, int unit,
+                                                   int nw, float2 ri, float& Fx, float& Fy, float& pe) {
     const PairConsts pc = a.pc;
     const PairConsts2 c2 = make_pair_consts2(pc);
     const int lane = threadIdx.x & 31;
     const float2 nri = make_float2(-ri.x, -ri.y);
     float2 acc = make_float2(0.0f, 0.0f), pe2 = acc;
-#pragma unroll
-    for (int u = 0; u < CL_NWPRE; ++u)
-        if (u < nw) word_eval<PE>(pc, c2, win, sw[u * 32 + lane], nri, acc, pe2);          // warp-uniform
-    for (int u = CL_NWPRE; u < nw; ++u)
-        word_eval<PE>(pc, c2, win, a.nb4[(size_t)u * a.Nalloc + i], nri, acc, pe2);
+    const int nws = min(nw, CL_NWS);
+    const unsigned swl = sw + lane * 4;
+#pragma unroll 2
+    for (int w = 0; w < nws; ++w) word_eval<PE>(pc, c2, win, lds32(swl + w * 128), nri, acc, pe2);
+    if (nw > CL_NWS) {
+        const unsigned* __restrict__ gw = a.nb4 + (size_t)unit * CL_UNITWORDS + lane;
+        for (int w = CL_NWS; w < nw; ++w) word_eval<PE>(pc, c2, win, gw[w * 32], nri, acc, pe2);
+    }
     Fx = -acc.x;
     Fy = -acc.y;
     if (PE) pe = pe2.x + pe2.y;
+}
+
+// slow path of a buffer wait (try_wait itself sleeps in hardware; this is only reached after its time
+// limit): kept out of line so that the unit loop carries one SYNCS + one branch
+__device__ __noinline__ void mbar_wait_slow(const CellsArgs& a, unsigned bar, unsigned par) {
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, par)) {
+        if (a.spin_limit > 0 && clock64() - t0 > a.spin_limit) { atomicExch(a.state + ST_ABORT, 3); break; }
+    }
 }
 
 struct StepFlags {
@@ -765,16 +820,25 @@ struct StepFlags {
     bool kick1, final, want_e, want_pe, want_ke, thermo, sample;
 };
 
+// per-warp pipeline state that outlives a step: shared-memory addresses and the mbarrier phases
+struct WarpPipe {
+    unsigned base;      // this warp's block: window buffer 0 | window buffer 1 | word buffer 0 | word buffer 1
+    unsigned bar;       // two mbarriers (8 bytes each), one per buffer
+    unsigned phase;     // bit b = parity the next wait on buffer b expects
+};
+
 // ---- one step's pass of one warp --------------------------------------------------------------------
 // A unit = 32 consecutive slots = one warp.  Warp gw evaluates units u_lo + gw + k * W (interleaved:
 // every warp sees units of ~28 different rows, which evens out density and edge effects; warps never
-// wait for each other inside a step).  Software pipeline, driven by cp.async: while unit k is
-// evaluated out of one shared-memory buffer, the windows and list words of unit k+1 are streaming
-// into the other one and the copy plan of unit k+2 is on its way to registers.
-template <bool PE>
+// wait for each other inside a step).  Software pipeline, driven by bulk copies: while unit k is
+// evaluated out of one shared-memory buffer, FOUR bulk copies of unit k+1 are in flight into the other
+// one (three neighbour windows + the unit's list words, issued by lanes 0-3, completion counted in
+// bytes on the buffer's mbarrier) and the copy plan of unit k+2 is on its way to registers.
+// PLAIN = an ordinary step of a run (second kick of the previous step, first kick + drift of this one;
+// no sample, no energies, no thermostat, not the last step): the flag tests are compiled out.
+template <bool PE, bool PLAIN>
 __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, const StepFlags& fl,
-                                          float2* wbuf /* [2][CL_WSLOTS] */, unsigned* swbuf /* [2][CL_NWPRE][32] */,
-                                          int& moved) {
+                                          WarpPipe& wp, int& moved) {
     const RunCtl& rc = a.rc;
     const int lane = threadIdx.x & 31;
     const int W = a.G * CL_WARPS, gw = blockIdx.x * CL_WARPS + (threadIdx.x >> 5);
@@ -783,6 +847,11 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
     float2* Rnext = a.R[ctx.pr ^ 1];
     float2* V = a.V[ctx.pv];
     const int* og = a.orig[ctx.pv];
+    const bool kick1  = PLAIN ? true  : fl.kick1;
+    const bool final  = PLAIN ? false : fl.final;
+    const bool thermo = PLAIN ? false : fl.thermo;
+    const bool sample = PLAIN ? false : fl.sample;
+    const bool want_ke = PLAIN ? false : fl.want_ke;
     // halo pushes (slabs): slots of my first / last owned row and where they live in the neighbours
     const int dn = (a.me + a.P - 1) % a.P, up = (a.me + 1) % a.P;
     int first_e = 0, last_s = 0, peer_hi_start = 0;
@@ -791,72 +860,87 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
         last_s = a.cell_start[(a.own_lo + a.nloc - 1) * a.nbx];
         peer_hi_start = __ldcg(&a.mail[MB_HI_START]);
     }
-    // the sentinel slots behind the staged windows (never within rc of anything)
+    // the sentinel slots behind the staged windows (never within rc of anything; the list build uses
+    // this memory for its byte rows, so they are rewritten every step)
     if (lane >= 28) {
-        wbuf[3 * CL_WIN + (lane & 3)] = make_float2(1.0e9f, 1.0e9f);
-        wbuf[CL_WSLOTS + 3 * CL_WIN + (lane & 3)] = make_float2(1.0e9f, 1.0e9f);
+        asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(wp.base + (3 * CL_WIN + (lane & 3)) * 8), "f"(1.0e9f) : "memory");
+        asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(wp.base + CL_WINBYTES + (3 * CL_WIN + (lane & 3)) * 8), "f"(1.0e9f) : "memory");
     }
     __syncwarp();
 
-    // copy plan of a unit: (ws0, ws1, ws2, staged) (wn0, wn1, wn2, nwords)
-    auto issue = [&](int u, const int4& p0, const int4& p1, int buf) {
-        if (u < u_hi && p0.w != 0) {
-            float2* win = wbuf + buf * CL_WSLOTS;
-            unsigned* sw = swbuf + buf * (CL_NWPRE * 32);
-#pragma unroll
-            for (int j = 0; j < CL_WIN; j += 32) {
-                if (j + lane < p1.x) cp_async8(win + j + lane, R + p0.x + j + lane);
-                if (j + lane < p1.y) cp_async8(win + CL_WIN + j + lane, R + p0.y + j + lane);
-                if (j + lane < p1.z) cp_async8(win + 2 * CL_WIN + j + lane, R + p0.z + j + lane);
+    // copy plan of a unit: (ws0, ws1, ws2, wn0 | wn1 << 8 | wn2 << 16 | nw << 24 | staged << 31).
+    // Lane k < 3 copies window k, lane 3 the list words; lane 0 arms the mbarrier with the byte total.
+    const char* Rbytes = reinterpret_cast<const char*>(R);
+    const char* Lbytes = reinterpret_cast<const char*>(a.nb4);
+    const unsigned my_dst = wp.base + (lane < 3 ? lane * (CL_WIN * 8) : 2 * CL_WINBYTES);   // + buf * stride
+    const unsigned my_stride = lane < 3 ? CL_WINBYTES : CL_SWBYTES;
+    auto issue = [&](int u, const int4& p, int buf) {
+        if (u < u_hi && p.w < 0) {
+            const unsigned pw = (unsigned)p.w;
+            const unsigned nws = min((pw >> 24) & 0x7fu, (unsigned)CL_NWS);
+            const unsigned bar = wp.bar + buf * 8;
+            if (lane == 0)
+                mbar_expect_tx(bar, ((pw & 0xffu) + ((pw >> 8) & 0xffu) + ((pw >> 16) & 0xffu)) * 8u + nws * 128u);
+            __syncwarp();
+            if (lane < 4) {
+                int ws = p.z;
+                ws = lane == 1 ? p.y : ws;
+                ws = lane == 0 ? p.x : ws;
+                unsigned bytes = ((pw >> (8 * lane)) & 0xffu) * 8u;
+                long long off = (long long)ws * 8;
+                const char* base = Rbytes;
+                if (lane == 3) { bytes = nws * 128u; off = (long long)u * (CL_UNITWORDS * 4); base = Lbytes; }
+                if (bytes) bulk_g2s(my_dst + buf * my_stride, base + off, bytes, bar);
             }
-            const int i = u * 32 + lane;
-#pragma unroll
-            for (int w = 0; w < CL_NWPRE; ++w)
-                if (w < p1.w) cp_async4(sw + w * 32 + lane, a.nb4 + (size_t)w * a.Nalloc + i);
         }
-        cp_async_commit();
     };
     // Schedule: the first ~60 % of the units statically interleaved (no traffic), the rest drawn one by
     // one from a per-step counter: warps that met several slow (edge) units take fewer of the tail.
     const int rounds0 = (int)(a.static_frac * (float)((u_hi - u_lo) / W));
     const int dyn_lo = u_lo + rounds0 * W;
-    auto grab = [&](int j) -> int {                       // j-th unit of this warp (value valid in lane 0
-        if (j < rounds0) return u_lo + gw + j * W;        //  for the dynamic part: broadcast before use)
+    // (the dynamic draw returns the RAW counter value of lane 0; `fix` adds the base after the broadcast,
+    //  a whole unit later, so that no instruction waits for the atomic's round trip to L2)
+    auto grab = [&](int j) -> int {                       // j-th unit of this warp, relative to base(j)
+        if (j < rounds0) return gw + j * W;
         int t = 0;
-        if (lane == 0) t = dyn_lo + atomicAdd(&a.sched[fl.par], 1);
+        if (lane == 0) t = atomicAdd(&a.sched[fl.par], 1);
         return t;
     };
+    auto fix = [&](int raw, int j) -> int { return raw + (j < rounds0 ? u_lo : dyn_lo); };
     const int4 z4 = make_int4(0, 0, 0, 0);
-    int u = __shfl_sync(0xffffffffu, grab(0), 0), un = __shfl_sync(0xffffffffu, grab(1), 0);
+    int u = fix(__shfl_sync(0xffffffffu, grab(0), 0), 0), un = fix(__shfl_sync(0xffffffffu, grab(1), 0), 1);
     int g = grab(2);                                      // drawn now, broadcast one unit later
-    int4 p0 = z4, p1 = z4, q0 = z4, q1 = z4;
-    if (u < u_hi) { p0 = a.wplan[2 * u]; p1 = a.wplan[2 * u + 1]; }
-    if (un < u_hi) { q0 = a.wplan[2 * un]; q1 = a.wplan[2 * un + 1]; }
-    issue(u, p0, p1, 0);
+    int4 p = z4, q = z4;
+    if (u < u_hi) p = a.wplan[u];
+    if (un < u_hi) q = a.wplan[un];
+    issue(u, p, 0);
 
     for (int k = 0; u < u_hi; ++k) {
         const int buf = k & 1;
-        issue(un, q0, q1, buf ^ 1);                       // next unit's windows + words
-        const int unn = __shfl_sync(0xffffffffu, g, 0);
+        issue(un, q, buf ^ 1);                            // next unit's windows + words
+        const int unn = fix(__shfl_sync(0xffffffffu, g, 0), k + 2);
         g = grab(k + 3);
-        int4 r0 = z4, r1 = z4;
-        if (unn < u_hi) { r0 = a.wplan[2 * unn]; r1 = a.wplan[2 * unn + 1]; }   // consumed next iteration
+        int4 r = z4;
+        if (unn < u_hi) r = a.wplan[unn];                 // consumed next iteration
         const int  i    = u * 32 + lane;
         const bool live = (i >= ctx.own_s) & (i < ctx.own_e);
         // epilogue operands requested now, consumed after the pair loop
         float2 v = make_float2(0.0f, 0.0f), rb = make_float2(0.0f, 0.0f);
-        if (live && rc.nsteps > 0) { v = V[i]; rb = a.Rb[i]; }
+        if (live && (PLAIN || rc.nsteps > 0)) { v = V[i]; rb = a.Rb[i]; }
         float2 ri = make_float2(0.0f, 0.0f);
         float Fx = 0.0f, Fy = 0.0f, pe = 0.0f, ke = 0.0f;
-        const int ii = live ? i : ctx.own_s;
-        cp_async_wait<1>();                               // this unit's copies have landed
-        __syncwarp();
-        if (p0.w != 0) {
-            const float2* win = wbuf + buf * CL_WSLOTS;
-            if (live) ri = win[CL_WIN + (i - p0.y)];      // own row window holds the own slot
-            bytes_force_staged<PE>(a, win, swbuf + buf * (CL_NWPRE * 32), ii, p1.w, ri, Fx, Fy, pe);
+        if (p.w < 0) {
+            // this unit's copies have landed when the buffer's mbarrier completes its phase
+            const unsigned bar = wp.bar + buf * 8, par = (wp.phase >> buf) & 1u;
+            if (!mbar_try_wait(bar, par)) mbar_wait_slow(a, bar, par);
+            wp.phase ^= 1u << buf;
+            const unsigned win = wp.base + buf * CL_WINBYTES;
+            if (live) ri = lds64(win + (CL_WIN + (i - p.y)) * 8);      // own row window holds the own slot
+            bytes_force_staged<PE>(a, win, wp.base + 2 * CL_WINBYTES + buf * CL_SWBYTES, u,
+                                   (int)(((unsigned)p.w >> 24) & 0x7fu), ri, Fx, Fy, pe);
         } else {
             unsigned meta = 0u;
+            const int ii = live ? i : ctx.own_s;
             if (live) { ri = R[i]; meta = a.meta[i]; }
             const int n = meta & 0xff;
             const bool wedge = __any_sync(0xffffffffu, (meta & 0x100u) != 0u);
@@ -864,14 +948,15 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
             else       list_force<PE, false>(a, R, ii, n, ri, Fx, Fy, pe);
         }
         if (live) {
-            if (fl.kick1) { v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt); }            // MD:74
-            if (fl.want_ke) ke = v.x * v.x + v.y * v.y;
-            const int o = (fl.sample || (fl.final && !fl.thermo)) ? og[i] : 0;
-            if (fl.sample) rc.traj[(size_t)(fl.s / rc.sample_every) * a.N + o] = ri;           // MD:93-100
-            if (fl.thermo) {
+            if (kick1) { v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt); }               // MD:74
+            if (want_ke) ke = v.x * v.x + v.y * v.y;
+            int o = 0;
+            if (!PLAIN) o = (sample || (final && !thermo)) ? og[i] : 0;
+            if (sample) rc.traj[(size_t)(fl.s / rc.sample_every) * a.N + o] = ri;              // MD:93-100
+            if (thermo) {
                 V[i] = v;
                 a.Fs[i] = make_float2(Fx, Fy);
-            } else if (fl.final) {
+            } else if (final) {
                 if (a.R_out) a.R_out[o] = ri;
                 if (a.V_out) a.V_out[o] = v;
                 if (a.F_out) a.F_out[o] = make_float2(Fx, Fy);
@@ -900,7 +985,7 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
         }
         // the warps that pushed halo particles order those peer stores at system scope now (hidden behind
         // the other warps' work) instead of every thread of the grid fencing at the end of the step
-        if (a.P > 1 && !fl.thermo && !fl.final) {
+        if (a.P > 1 && !thermo && !final) {
             const bool pushed = live && (i < first_e || i >= last_s);
             if (__any_sync(0xffffffffu, pushed)) __threadfence_system();
         }
@@ -909,14 +994,13 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
             const float t = warp_sum(live ? pe : 0.0f);       // (idle lanes of a boundary unit evaluate a dummy)
             if (lane == 0) __stcg(&a.pe_part[fl.par * a.nchunks + (u - u_lo)], t);
         }
-        if (fl.want_ke) {
+        if (want_ke) {
             const float t = warp_sum(ke);
             if (lane == 0) __stcg(&a.ke_part[fl.par * a.nchunks + (u - u_lo)], t);
         }
         __syncwarp();                                     // all lanes are done with `buf`
-        u = un; un = unn; p0 = q0; p1 = q1; q0 = r0; q1 = r1;
+        u = un; un = unn; p = q; q = r;
     }
-    cp_async_wait<0>();
 }
 
 extern __shared__ __align__(16) unsigned char cells_smem[];
@@ -927,6 +1011,7 @@ cells_persistent_kernel(const CellsArgs a) {
     __shared__ double sdbl[CL_THREADS / 32];
     __shared__ float  s_lambda;
     __shared__ long long s_pt[12];
+    __shared__ __align__(8) unsigned long long s_mbar[CL_WARPS][2];
     const int tid = threadIdx.x, gtid = blockIdx.x * CL_THREADS + tid, gsz = a.G * CL_THREADS;
     const RunCtl rc = a.rc;
     Ctx ctx;
@@ -939,12 +1024,22 @@ cells_persistent_kernel(const CellsArgs a) {
     ctx.own_s = a.state[ST_OWN_S];
     ctx.own_e = a.state[ST_OWN_E];
     ctx.xepoch = (unsigned)a.state[ST_XEPOCH];
-    // per warp: staged neighbour windows (+ sentinel slots) and the byte rows of the list build
-    // (window buffer 0 | window buffer 1 | word buffers; the list build lays its byte rows over
-    //  everything behind window buffer 0)
+    // per warp: two window buffers (+ sentinel slots) and two word buffers, filled by bulk copies; the
+    // list build uses window buffer 0 and lays its byte rows over everything behind it
     float2* my_win = reinterpret_cast<float2*>(cells_smem + (size_t)(tid >> 5) * CL_WARP_SMEM);
-    unsigned char* my_bytes = cells_smem + (size_t)(tid >> 5) * CL_WARP_SMEM + CL_WSLOTS * 8;
-    unsigned* my_words = reinterpret_cast<unsigned*>(cells_smem + (size_t)(tid >> 5) * CL_WARP_SMEM + 2 * CL_WSLOTS * 8);
+    unsigned char* my_bytes = cells_smem + (size_t)(tid >> 5) * CL_WARP_SMEM + CL_WINBYTES;
+    WarpPipe wp;
+    // (the two addresses pass through an opaque move: ptxas otherwise rebuilds them from the CTA's
+    //  shared window and the warp index at every use instead of keeping two registers)
+    asm volatile("mov.u32 %0, %1;" : "=r"(wp.base) : "r"(smem_u32(my_win)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(wp.bar) : "r"(smem_u32(&s_mbar[tid >> 5][0])));
+    wp.phase = 0u;
+    if ((tid & 31) == 0) {
+        mbar_init(wp.bar, 1);
+        mbar_init(wp.bar + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     if (a.s_begin < 0) {
         // load the caller's state (original order) and sort it.  Slabs: every rank reads the whole
@@ -1010,8 +1105,12 @@ cells_persistent_kernel(const CellsArgs a) {
         const int u_lo = ctx.own_s >> 5, u_hi = (ctx.own_e + 31) >> 5;      // 32-slot units
         if (gtid == 0) __stcg(&a.sched[par ^ 1], 0);     // the other parity's unit counter: idle this step
         int moved = 0;
-        if (want_pe) warp_pass<true >(a, ctx, fl, my_win, my_words, moved);
-        else         warp_pass<false>(a, ctx, fl, my_win, my_words, moved);
+        if (want_pe)
+            warp_pass<true, false>(a, ctx, fl, wp, moved);
+        else if (kick1 && !final && !thermo && !sample && !want_ke)
+            warp_pass<false, true>(a, ctx, fl, wp, moved);
+        else
+            warp_pass<false, false>(a, ctx, fl, wp, moved);
         if (thermo) {
             CL_BARRIER();
             const double ke2 = block_sum_array(a.ke_part + par * a.nchunks, u_hi - u_lo, sdbl);
@@ -1162,7 +1261,7 @@ int cells_create(ljmd_handle* h) {
     cl->ncells = cl->nlr * cl->nbx;
     cl->ncells_max = (maxloc + 2 * cl->own_lo) * cl->nbx;
     if (P == 1) {
-        cl->Nalloc = (int)(((N + 63) / 64) * 64);
+        cl->Nalloc = (int)(((N + 2 + 63) / 64) * 64);    // (+2: a bulk copy may read one slot past a window)
     } else {
         // owned rows + two halo rows, with room for density fluctuations between slabs
         const double per = (double)N / P;
@@ -1211,7 +1310,7 @@ int cells_create(ljmd_handle* h) {
     LJ_CUDA(cudaMalloc(&cl->tmpc, sizeof(int) * na));
     LJ_CUDA(cudaMalloc(&cl->meta, sizeof(unsigned) * na));
     LJ_CUDA(cudaMalloc(&cl->ent, sizeof(uint2) * na * CL_E));
-    LJ_CUDA(cudaMalloc(&cl->wplan, sizeof(int4) * 2 * (na / 32 + 1)));
+    LJ_CUDA(cudaMalloc(&cl->wplan, sizeof(int4) * (na / 32 + 1)));
     LJ_CUDA(cudaMalloc(&cl->nb4, sizeof(unsigned) * na * CL_NW));
     LJ_CUDA(cudaMalloc(&cl->cell_start, sizeof(int) * ((size_t)cl->ncells + 1)));
     LJ_CUDA(cudaMalloc(&cl->row_tot, sizeof(int) * (size_t)cl->nlr));
