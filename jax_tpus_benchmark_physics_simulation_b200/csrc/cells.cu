@@ -50,7 +50,10 @@ namespace ljmd {
 namespace {
 
 constexpr int CL_B5 = 3;          // slots per thread per trip of the rebuild gather (B5)
-constexpr int CL_THREADS   = 512;
+#ifndef CL_THREADS_
+#define CL_THREADS_ 512
+#endif
+constexpr int CL_THREADS   = CL_THREADS_;
 constexpr int CL_K         = 4;     // bins per (rc + skin)
 constexpr int CL_E         = 8;     // list entries per particle (3 when every range fits 32 slots)
 constexpr int CL_WIN       = 84;    // staged window capacity per stencil row and warp (slots):
@@ -68,10 +71,15 @@ constexpr int CL_BROW      = 4 * CL_NW + 4;   // a lane's byte row while a list 
 constexpr int CL_WINBYTES  = CL_WSLOTS * 8;                 // 2048
 constexpr int CL_SWBYTES   = CL_NWS * 32 * 4;               // 1280
 constexpr int CL_WARP_SMEM = 2 * CL_WINBYTES + 2 * CL_SWBYTES;   // bytes per warp (6656)
+#ifndef CL_UNROLL
+#define CL_UNROLL 2
+#endif
+constexpr int CL_WORD_UNROLL = CL_UNROLL;                   // list words per trip of the pair loop
 constexpr int CL_UNITWORDS = CL_NW * 32;                    // list words of one 32-slot unit in nb4
 static_assert(CL_WINBYTES + 32 * CL_BROW <= CL_WARP_SMEM, "byte rows must fit behind window buffer 0");
 static_assert(CL_WARP_SMEM % 16 == 0 && CL_WIN % 2 == 0, "bulk copies need 16-byte granularity");
 constexpr int CL_WARPS     = CL_THREADS / 32;
+constexpr int CL_QMAX      = 1024;  // unit queues: one per SM in use (indexed by a compact SM number)
 constexpr int CL_ORDER_MAX = 64;    // cells denser than this keep arrival order (see B5)
 
 enum { ST_PR = 0, ST_PV = 1, ST_REBUILDS = 2, ST_ERR = 3, ST_FLAG = 4, ST_NHELD = 5, ST_OWN_S = 6,
@@ -111,7 +119,8 @@ struct CellsArgs {
     unsigned* nb4;                  // byte lists of staged units, nb4[(unit * CL_NW + w) * 32 + lane]
     int4*     wplan;                // per unit: (ws0, ws1, ws2, wn0 | wn1 << 8 | wn2 << 16 | nw << 24 | staged << 31)
     float  *pe_part, *ke_part;      // [2*nchunks] per-unit partials (by step parity); nchunks = unit capacity
-    int*      sched;                // [2] chunk counters (by step parity)
+    int*      sched;                // [2][CL_QMAX] unit counters (by step parity, per SM queue) | [CL_QMAX] SM id ->
+                                    // queue table | queue count (see the kernel prologue)
     int*      state;                // ST_* words
     unsigned* bar;
     const float2* R_in;
@@ -210,6 +219,7 @@ struct Ctx {
     int nheld;          // local slots in use (owned rows + halo rows)
     int own_s, own_e;   // slot range of the owned rows
     long long* pt;      // shared-memory phase clocks (thread 0), or nullptr
+    int q, nq;          // this SM's unit queue and the number of queues
 };
 
 // ---- cross-GPU synchronisation (slab decomposition) -----------------------------------------------
@@ -248,7 +258,7 @@ __device__ __forceinline__ bool peer_sync(const CellsArgs& a, Ctx& ctx, bool pay
     const bool r = s_any != 0;
     __syncthreads();
     // the peers' halo stores are read by bulk copies (async proxy) from here on
-    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("fence.proxy.async.global;" ::: "memory");
     return r;
 }
 
@@ -265,9 +275,9 @@ __device__ __forceinline__ bool peer_sync(const CellsArgs& a, Ctx& ctx, bool pay
 //  the barrier, see fence_proxy_async)
 #define CL_BARRIER()                                                                                  \
     do {                                                                                              \
-        asm volatile("fence.proxy.async;" ::: "memory");                                              \
+        asm volatile("fence.proxy.async.global;" ::: "memory");                                              \
         grid_barrier(a.bar, (++ctx.epoch) * (unsigned)a.G, a.state + ST_ABORT, a.spin_limit);         \
-        asm volatile("fence.proxy.async;" ::: "memory");                                              \
+        asm volatile("fence.proxy.async.global;" ::: "memory");                                              \
     } while (0)
 
 // ---- rebuild: counting sort by cell, deterministic in-cell order, bitmask Verlet list --------------
@@ -755,7 +765,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
 }
 // generic-proxy writes (st.global of the integrate epilogue / the rebuild) must be ordered against the
 // async-proxy reads of later bulk copies: one proxy fence on each side of every grid barrier
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 __device__ __forceinline__ float2 lds64(unsigned addr) {
     float2 v;
@@ -794,7 +804,7 @@ __device__ __forceinline__ void bytes_force_staged(const CellsArgs& a, unsigned 
     float2 acc = make_float2(0.0f, 0.0f), pe2 = acc;
     const int nws = min(nw, CL_NWS);
     const unsigned swl = sw + lane * 4;
-#pragma unroll 2
+#pragma unroll CL_WORD_UNROLL
     for (int w = 0; w < nws; ++w) word_eval<PE>(pc, c2, win, lds32(swl + w * 128), nri, acc, pe2);
     if (nw > CL_NWS) {
         const unsigned* __restrict__ gw = a.nb4 + (size_t)unit * CL_UNITWORDS + lane;
@@ -903,10 +913,12 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
     auto grab = [&](int j) -> int {                       // j-th unit of this warp, relative to base(j)
         if (j < rounds0) return gw + j * W;
         int t = 0;
-        if (lane == 0) t = atomicAdd(&a.sched[fl.par], 1);
+        if (lane == 0) t = atomicAdd(&a.sched[fl.par * CL_QMAX + ctx.q], 1);
         return t;
     };
-    auto fix = [&](int raw, int j) -> int { return raw + (j < rounds0 ? u_lo : dyn_lo); };
+    // dynamic units are dealt round-robin to the SM queues: the CTAs that share an SM (and its issue
+    // slots, which the warp arbiter does not hand out evenly) draw from the same counter
+    auto fix = [&](int raw, int j) -> int { return j < rounds0 ? raw + u_lo : dyn_lo + ctx.q + ctx.nq * raw; };
     const int4 z4 = make_int4(0, 0, 0, 0);
     int u = fix(__shfl_sync(0xffffffffu, grab(0), 0), 0), un = fix(__shfl_sync(0xffffffffu, grab(1), 0), 1);
     int g = grab(2);                                      // drawn now, broadcast one unit later
@@ -1005,7 +1017,7 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
 
 extern __shared__ __align__(16) unsigned char cells_smem[];
 
-__global__ void __launch_bounds__(CL_THREADS, 2)
+__global__ void __launch_bounds__(CL_THREADS, 1024 / CL_THREADS)
 cells_persistent_kernel(const CellsArgs a) {
     __shared__ int    sscan[CL_THREADS / 32 + 1];
     __shared__ double sdbl[CL_THREADS / 32];
@@ -1039,7 +1051,34 @@ cells_persistent_kernel(const CellsArgs a) {
         mbar_init(wp.bar + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    // unit queues: the CTAs resident on one SM share a queue.  The first CTA of an SM to get here takes
+    // the next queue number and publishes it in the SM's table entry (the launch is cooperative, so the
+    // CTA being waited for is resident).  Table and count are zeroed by the host before every launch.
+    {
+        __shared__ int s_q;
+        if (tid == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            int* tab = a.sched + 2 * CL_QMAX;
+            int* qcount = tab + CL_QMAX;
+            const int slot = (int)(smid % CL_QMAX);
+            int v = atomicCAS(&tab[slot], 0, -1);
+            if (v == 0) {
+                v = atomicAdd(qcount, 1) + 1;
+                atomicExch(&tab[slot], v);
+            } else {
+                const long long t0 = clock64();
+                while ((v = atomicAdd(&tab[slot], 0)) <= 0) {
+                    if (a.spin_limit > 0 && clock64() - t0 > a.spin_limit) { atomicExch(a.state + ST_ABORT, 1); v = 1; break; }
+                }
+            }
+            s_q = v - 1;
+        }
+        __syncthreads();
+        ctx.q = s_q;
+    }
+    CL_BARRIER();
+    ctx.nq = max(1, __ldcg(a.sched + 3 * CL_QMAX));
 
     if (a.s_begin < 0) {
         // load the caller's state (original order) and sort it.  Slabs: every rank reads the whole
@@ -1103,7 +1142,7 @@ cells_persistent_kernel(const CellsArgs a) {
         fl.s = s; fl.par = par; fl.kick1 = kick1; fl.final = final; fl.want_e = want_e; fl.want_pe = want_pe;
         fl.want_ke = want_ke; fl.thermo = thermo; fl.sample = sample;
         const int u_lo = ctx.own_s >> 5, u_hi = (ctx.own_e + 31) >> 5;      // 32-slot units
-        if (gtid == 0) __stcg(&a.sched[par ^ 1], 0);     // the other parity's unit counter: idle this step
+        if (gtid < CL_QMAX) __stcg(&a.sched[(par ^ 1) * CL_QMAX + gtid], 0);   // the other parity's unit counters: idle this step
         int moved = 0;
         if (want_pe)
             warp_pass<true, false>(a, ctx, fl, wp, moved);
@@ -1319,7 +1358,7 @@ int cells_create(ljmd_handle* h) {
     LJ_CUDA(cudaMalloc(&cl->state, sizeof(int) * ST_WORDS));
     LJ_CUDA(cudaMemset(cl->state, 0, sizeof(int) * ST_WORDS));
     LJ_CUDA(cudaMalloc(&cl->bar, sizeof(unsigned)));
-    LJ_CUDA(cudaMalloc(&cl->sched, sizeof(int) * 2));
+    LJ_CUDA(cudaMalloc(&cl->sched, sizeof(int) * (3 * CL_QMAX + 1)));
     if (getenv("LJMD_CELLS_PROF")) LJ_CUDA(cudaMalloc(&cl->prof, sizeof(long long) * 12 * cl->G));
     return 0;
 }
@@ -1348,7 +1387,8 @@ static void fill_args(ljmd_handle* h, CellsArgs& a) {
     a.inv_hy = cl->inv_hy; a.inv_wx = cl->inv_wx;
     a.rlist2 = cl->rlist * cl->rlist;
     a.half_skin2 = (0.5f * h->p.skin) * (0.5f * h->p.skin);
-    a.static_frac = 0.6f;      // measured at N = 4M: 0.0 -> 170.3, 0.5 -> 160.4, 0.7 -> 161.4, 0.9 -> 171.0, 1.0 -> 174.7 us/step
+    a.static_frac = 0.5f;      // measured at N = 4M (liquid, 300-step calls, per-SM queues): 0.0 -> 145.8, 0.2 -> 143.4,
+                               // 0.4 -> 142.8, 0.6 -> 142.6, 0.8 -> 144.2 us/step (one global queue: 0.4 -> 154.2, 0.8 -> 143.9)
     if (const char* e = getenv("LJMD_CELLS_STATIC")) a.static_frac = fminf(1.0f, fmaxf(0.0f, (float)atof(e)));
     a.dt = h->p.dt;
     a.spin_limit = h->spin_limit;
@@ -1377,7 +1417,7 @@ static void fill_args(ljmd_handle* h, CellsArgs& a) {
 static int launch(ljmd_handle* h, CellsArgs& a) {
     Cells* cl = h->cells;
     LJ_CUDA(cudaMemsetAsync(cl->bar, 0, sizeof(unsigned), h->stream));
-    LJ_CUDA(cudaMemsetAsync(cl->sched, 0, sizeof(int) * 2, h->stream));
+    LJ_CUDA(cudaMemsetAsync(cl->sched, 0, sizeof(int) * (3 * CL_QMAX + 1), h->stream));
     void* args[] = {(void*)&a};
     LJ_CUDA(cudaLaunchCooperativeKernel((void*)cells_persistent_kernel, dim3(cl->G), dim3(CL_THREADS),
                                         args, (size_t)CL_WARPS * CL_WARP_SMEM, h->stream));
