@@ -86,7 +86,14 @@ enum { ST_PR = 0, ST_PV = 1, ST_REBUILDS = 2, ST_ERR = 3, ST_FLAG = 4, ST_NHELD 
        ST_OWN_E = 7, ST_LOADCNT = 8, ST_XEPOCH = 9, ST_LMOVED = 10, ST_ABORT = 11, ST_WORDS = 16 };
 // ST_ERR: conditions that void the RESULT (the kernel itself keeps running in lockstep);
 // ST_ABORT: a spin wait gave up (1 = grid barrier, 2 = peer GPU) - later waits fall through
-enum { CERR_LIST_OVERFLOW = 2, CERR_CAPACITY = 8 };
+enum { CERR_LIST_OVERFLOW = 2, CERR_CAPACITY = 8, CERR_DEBUG = 16 };
+// -DLJMD_DEBUG_CHECKS: in-kernel bounds assertions on every window, list index and bulk copy (the stand-in for
+// compute-sanitizer memcheck, which is closed on the measurement pool); a violation raises CERR_DEBUG
+#ifdef LJMD_DEBUG_CHECKS
+#define CL_ASSERT(cond) do { if (!(cond)) atomicOr(a.state + ST_ERR, CERR_DEBUG); } while (0)
+#else
+#define CL_ASSERT(cond) do { } while (0)
+#endif
 // mailbox words a neighbour writes (slab decomposition)
 enum { MB_HI_START = 0, MB_WORDS = 8 };
 
@@ -565,6 +572,13 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
                     staged = staged && (wn[k] <= CL_WIN);
                 }
             }
+            if (staged) {
+                for (int k = 0; k < 3; ++k) {
+                    CL_ASSERT(ws[k] >= 0 && wn[k] >= 0 && ws[k] + wn[k] <= a.Nalloc && (ws[k] & 1) == 0 && (wn[k] & 1) == 0);
+                    CL_ASSERT(!live || (cs_s[k] >= ws[k] && cs_e[k] <= ws[k] + wn[k] && cs_s[k] <= cs_e[k]));
+                }
+                CL_ASSERT(!live || (i >= ws[1] && i < ws[1] + wn[1]));
+            }
             int plan_w = staged ? (int)(0x80000000u | (unsigned)wn[0] | ((unsigned)wn[1] << 8) | ((unsigned)wn[2] << 16)) : 0;
             int n = 0, cnt = 0;
             if (staged) {
@@ -621,6 +635,7 @@ __device__ void cells_rebuild(const CellsArgs& a, Ctx& ctx, int* sscan, float2* 
                     for (int q = min(nn, 4 * CL_NW); q < 4 * nwmax; ++q) myb[q] = (unsigned char)CL_DUMMY;
                     if (nw > CL_NW) atomicOr(a.state + ST_ERR, CERR_LIST_OVERFLOW);
                     const unsigned* myw = reinterpret_cast<const unsigned*>(myb);
+                    CL_ASSERT((size_t)(i0 >> 5) * CL_UNITWORDS + (size_t)(nwmax - 1) * 32 + lane < (size_t)a.Nalloc * CL_NW || nwmax == 0);
                     unsigned* dst = a.nb4 + (size_t)(i0 >> 5) * CL_UNITWORDS + lane;
                     for (int u = 0; u < nwmax; ++u) dst[u * 32] = myw[u];
                 }
@@ -763,9 +778,9 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// generic-proxy writes (st.global of the integrate epilogue / the rebuild) must be ordered against the
-// async-proxy reads of later bulk copies: one proxy fence on each side of every grid barrier
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+// (generic-proxy writes - st.global of the integrate epilogue / the rebuild / peer GPUs - are ordered against
+//  the async-proxy reads of later bulk copies by one fence.proxy.async.global on each side of every grid
+//  barrier and after every cross-GPU sync: CL_BARRIER, peer_sync)
 
 __device__ __forceinline__ float2 lds64(unsigned addr) {
     float2 v;
@@ -900,6 +915,9 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
                 long long off = (long long)ws * 8;
                 const char* base = Rbytes;
                 if (lane == 3) { bytes = nws * 128u; off = (long long)u * (CL_UNITWORDS * 4); base = Lbytes; }
+                CL_ASSERT(lane == 3 ? (off >= 0 && off + bytes <= (long long)a.Nalloc * CL_NW * 4)
+                                    : (off >= 0 && off + bytes <= (long long)a.Nalloc * 8 && bytes <= CL_WIN * 8));
+                CL_ASSERT((off & 15) == 0 && (bytes & 15) == 0);
                 if (bytes) bulk_g2s(my_dst + buf * my_stride, base + off, bytes, bar);
             }
         }
@@ -947,6 +965,21 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
             if (!mbar_try_wait(bar, par)) mbar_wait_slow(a, bar, par);
             wp.phase ^= 1u << buf;
             const unsigned win = wp.base + buf * CL_WINBYTES;
+            CL_ASSERT(!live || (i - p.y >= 0 && i - p.y < (int)(((unsigned)p.w >> 8) & 0xffu)));
+#ifdef LJMD_DEBUG_CHECKS
+            if (live) {   // every listed index names a staged slot of its window or the sentinel
+                const unsigned pw = (unsigned)p.w;
+                const int nwd = (int)((pw >> 24) & 0x7fu);
+                for (int w = 0; w < nwd; ++w) {
+                    const unsigned word = a.nb4[(size_t)u * CL_UNITWORDS + w * 32 + lane];
+                    for (int b = 0; b < 4; ++b) {
+                        const int idx = (int)((word >> (8 * b)) & 0xffu);
+                        const int k = idx / CL_WIN;
+                        CL_ASSERT(idx == CL_DUMMY || (k < 3 && idx - k * CL_WIN < (int)((pw >> (8 * k)) & 0xffu)));
+                    }
+                }
+            }
+#endif
             if (live) ri = lds64(win + (CL_WIN + (i - p.y)) * 8);      // own row window holds the own slot
             bytes_force_staged<PE>(a, win, wp.base + 2 * CL_WINBYTES + buf * CL_SWBYTES, u,
                                    (int)(((unsigned)p.w >> 24) & 0x7fu), ri, Fx, Fy, pe);
@@ -1571,6 +1604,10 @@ int cells_check_error(ljmd_handle* h) {
     if (e[ST_ERR] & CERR_CAPACITY) {
         set_error("cell-list: a slab holds more particles than its buffers (density too uneven over the GPUs)");
         return LJMD_E_OVERFLOW;
+    }
+    if (e[ST_ERR] & CERR_DEBUG) {
+        set_error("cell-list: a debug bounds assertion failed (LJMD_DEBUG_CHECKS build)");
+        return LJMD_E_STATE;
     }
     return 0;
 }
