@@ -572,7 +572,7 @@ def main():
             "metric": "particle-steps/sec", "value": m["value"], "unit": "particle-steps/s",
             "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": m["ms_per_step"], "higher_is_better": True,
-            "scaling": "strong" if m["sharded"] else "weak", "vs_baseline": None, "dtype": "f32",
+            "scaling": "strong" if m["N"] >= SHARD_MIN_N else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic lattice+jitter (seed 0, jitter 0.05, kT 1.0)",
             "config": {"workload": wl_name, "desc": m["desc"], "N": m["N"], "rc": m["rc"], "dt": m["dt"],
                        "md_steps_per_step": m["md_steps_per_step"], "path": m["path"],

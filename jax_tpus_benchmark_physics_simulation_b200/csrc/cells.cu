@@ -234,6 +234,11 @@ struct Ctx {
 // payload bit) into every peer over NVLink after a system-scope fence, then every CTA waits until
 // all P local words carry the epoch.  Returns the OR of the payload bits.  Call after a grid barrier
 // (all of this rank's peer stores are then ordered before the stamp).
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ bool peer_sync(const CellsArgs& a, Ctx& ctx, bool payload) {
     const unsigned xe = ++ctx.xepoch;
     const int slot = (int)(xe & 1u) * a.P;          // words alternate by epoch: a peer that is already one
@@ -244,22 +249,27 @@ __device__ __forceinline__ bool peer_sync(const CellsArgs& a, Ctx& ctx, bool pay
         *f = (xe << 1) | (payload ? 1u : 0u);
     }
     __shared__ int s_any;
-    if (threadIdx.x == 0) {
-        const volatile unsigned* mine = a.peer_flags[a.me] + slot;
-        int any = payload ? 1 : 0;
-        long long t0 = clock64();
-        for (int q = 0; q < a.P; ++q) {
-            if (q == a.me) continue;
-            unsigned w;
-            while (((w = mine[q]) >> 1) != xe) {
-                if ((a.spin_limit > 0 && clock64() - t0 > 2 * a.spin_limit) || __ldcg(a.state + ST_ABORT) != 0) {
-                    atomicExch(a.state + ST_ABORT, 2); w = 0u; break;
-                }
+    if (threadIdx.x < 32) {
+        // lane q polls the word of rank q: all P words are in flight together, so a sync whose words
+        // have already landed costs ONE round trip to L2 (it used to be P - 1 dependent ones)
+        const int q = (int)threadIdx.x;
+        const bool mine_too = (q < a.P) && (q != a.me);
+        const unsigned* word = a.peer_flags[a.me] + slot + (mine_too ? q : 0);
+        unsigned w = (q == a.me && payload) ? 1u : 0u;
+        const long long t0 = clock64();
+        for (;;) {
+            bool done = true;
+            if (mine_too) { w = ld_acquire_sys(word); done = (w >> 1) == xe; }
+            if (__all_sync(0xffffffffu, done)) break;
+            const bool giveup = (a.spin_limit > 0 && clock64() - t0 > 2 * a.spin_limit) || __ldcg(a.state + ST_ABORT) != 0;
+            if (__any_sync(0xffffffffu, giveup)) {           // (warp-uniform exit)
+                if (q == 0) atomicExch(a.state + ST_ABORT, 2);
+                w = 0u;
+                break;
             }
-            any |= (int)(w & 1u);
         }
-        __threadfence_system();
-        s_any = any;
+        const bool any = __any_sync(0xffffffffu, (q < a.P) && (w & 1u) != 0u);
+        if (q == 0) s_any = any ? 1 : 0;
     }
     __syncthreads();
     const bool r = s_any != 0;
@@ -1218,6 +1228,7 @@ cells_persistent_kernel(const CellsArgs a) {
         if (!final) ctx.pr ^= 1;
         CL_PROF(0);
         CL_BARRIER();
+        CL_PROF(1);
         if (a.P > 1 && !final) {
             // one NVLink round trip per step: every rank's halo pushes have landed once all arrival
             // words carry this epoch; the words also carry "one of my particles left its skin/2 ball",
@@ -1227,7 +1238,7 @@ cells_persistent_kernel(const CellsArgs a) {
             if (any && gtid == 0) __stcg(a.state + ST_FLAG, (int)(s + 2));
             if (any) CL_BARRIER();                           // (rare) the flag is read at the next step
         }
-        CL_PROF(1);
+        CL_PROF(8);
 
         if (blockIdx.x == 0 && want_pe) {
             const double pe2 = block_sum_array(a.pe_part + par * a.nchunks, u_hi - u_lo, sdbl);
@@ -1521,9 +1532,9 @@ int cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_
         LJ_CUDA(cudaStreamSynchronize(st));
         std::vector<long long> pv(12 * cl->G);
         LJ_CUDA(cudaMemcpy(pv.data(), cl->prof, sizeof(long long) * pv.size(), cudaMemcpyDeviceToHost));
-        const char* nm[8] = {"force+integrate", "step barrier", "B1 bin+hist", "B2 row totals",
-                             "B3 scan", "B4 scatter", "B5 order+gather", "B6 list build"};
-        for (int k = 0; k < 8; ++k) {
+        const char* nm[9] = {"force+integrate", "step barrier", "B1 bin+hist", "B2 row totals",
+                             "B3 scan", "B4 scatter", "B5 order+gather", "B6 list build", "cross-GPU sync"};
+        for (int k = 0; k < 9; ++k) {
             double mean = 0, mx = 0;
             for (int c = 0; c < cl->G; ++c) { mean += pv[c * 12 + k]; mx = std::max<double>(mx, (double)pv[c * 12 + k]); }
             fprintf(stderr, "[ljmd cells prof] %-16s mean %12.0f  max %12.0f clocks (launch total)\n", nm[k], mean / cl->G, mx);
