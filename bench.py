@@ -222,7 +222,7 @@ def run_reference(args, wl_name, wl):
         "impl": "reference", "metric": "particle-steps/sec", "value": value,
         "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
-        "scaling": "strong" if (args.gpus > 1 and N >= SHARD_MIN_N) else "weak",
+        "scaling": "strong" if N >= SHARD_MIN_N else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic lattice+jitter (seed 0, jitter 0.05, kT 1.0)",
         "config": {"workload": wl_name, "desc": wl["desc"], "N": N, "rc": rc, "dt": dt,
                    "md_steps_per_step": 1, "path": wl["path"]},

@@ -114,6 +114,19 @@ int ljmd_run(ljmd_t* h, const float* R_in, const float* V_in, float* R_out, floa
 int ljmd_gr_hist(ljmd_t* h, const float* R_hist, int64_t S, int32_t nbins,
                  const float* edges, int64_t* counts);
 
+/* ---- the other dense pairwise kernels of the reference repo -------- */
+/* All-pairs acceleration with the pair law as a functor: gravity r^-3 in an open plane.
+ *   LJMD_LAW_GRAVITY_NBODY  pairwise_forces(positions, masses) of nbody_bh_merger_sim (NBODY:54-67):
+ *       a_i = sum_{j != i} where(r >= 1e-6, G m_j / r^3, 0) (pos_j - pos_i), summed in j order
+ *   LJMD_LAW_GRAVITY_EM3    the gravity term of acceleration() of three_particles_em_nonuni (EM3:25-38):
+ *       a_i = sum_j G m_j (pos_j - pos_i) max(r^2 + [i == j], 1e-12)^(-3/2)
+ * pos, acc: device (n,2) float32; mass: device float32[n]; enqueued on `stream` (cudaStream_t, may be
+ * NULL), no handle needed.  fp32 with every operation rounded once, as in the reference.            */
+#define LJMD_LAW_GRAVITY_NBODY 0
+#define LJMD_LAW_GRAVITY_EM3   1
+int ljmd_pair_accel(int32_t law, const float* pos, const float* mass, int64_t n, float G, float* acc,
+                    void* stream);
+
 /* ---- cell-list introspection (for the bit-exact CPU recount, north_star) -------- */
 /* geometry chosen at create: the box is cut into `nrows` rows of height >= rc+skin and each row
  * into `nbins_x` bins of width >= (rc+skin)/kbins; cell id = row * nbins_x + bin with

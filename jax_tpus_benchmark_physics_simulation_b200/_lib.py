@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("LJMD_LIB", os.path.join(_HERE, "libljmd.so"))   # LJM
 
 LJMD_PATH_AUTO, LJMD_PATH_ALLPAIRS, LJMD_PATH_CELLS = 0, 1, 2
 LJMD_E_OVERFLOW, LJMD_E_TIMEOUT = -6, -7
+LJMD_LAW_GRAVITY_NBODY, LJMD_LAW_GRAVITY_EM3 = 0, 1
 
 # every symbol include/ljmd.h declares (checked by tests/test_abi.py)
 EXPORTS = (
@@ -21,7 +22,7 @@ EXPORTS = (
     "ljmd_forces", "ljmd_run", "ljmd_gr_hist", "ljmd_cell_geometry", "ljmd_cell_assign",
     "ljmd_neighbor_count", "ljmd_last_rebuilds", "ljmd_get_unique_id", "ljmd_create_dist",
     "ljmd_last_run_ms", "ljmd_launch_count", "ljmd_fp32_peak_probe", "ljmd_allpairs_mode",
-    "ljmd_check",
+    "ljmd_check", "ljmd_pair_accel",
 )
 
 
@@ -86,6 +87,7 @@ def load() -> ctypes.CDLL:
     lib.ljmd_launch_count.argtypes = [vp, ctypes.POINTER(i64)]
     lib.ljmd_allpairs_mode.argtypes = [vp, ctypes.POINTER(i32)]
     lib.ljmd_fp32_peak_probe.argtypes = [i32, i32, ctypes.POINTER(f32)]
+    lib.ljmd_pair_accel.argtypes = [i32, vp, vp, i64, f32, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("ljmd_last_error", "ljmd_destroy"):

@@ -237,6 +237,12 @@ int ljmd_launch_count(ljmd_t* h, int64_t* launches) {
     return 0;
 }
 
+int ljmd_pair_accel(int32_t law, const float* pos, const float* mass, int64_t n, float G, float* acc,
+                    void* stream) {
+    return pairlaw_accel(law, reinterpret_cast<const float2*>(pos), mass, n, G,
+                         reinterpret_cast<float2*>(acc), reinterpret_cast<cudaStream_t>(stream));
+}
+
 int ljmd_fp32_peak_probe(int32_t device, int32_t packed, float* tflops) {
     if (!tflops) { set_error("null argument"); return LJMD_E_INVALID; }
     return fp32_peak_probe(device, packed, tflops);

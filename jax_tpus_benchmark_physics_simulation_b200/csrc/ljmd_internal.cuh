@@ -115,6 +115,10 @@ int  dist_allgather(ljmd_handle* h, void* buf, size_t bytes_per_rank);   // in p
 int  dist_allreduce_f32(ljmd_handle* h, float* buf, size_t n);
 int  dist_barrier(ljmd_handle* h);                      // cross-rank barrier in stream order
 
+// pairlaw.cu
+int  pairlaw_accel(int law, const float2* pos, const float* mass, long long n, float G, float2* acc,
+                   cudaStream_t stream);
+
 // probe.cu
 int  fp32_peak_probe(int device, int packed, float* tflops);
 

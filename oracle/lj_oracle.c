@@ -301,3 +301,39 @@ void orc_gr_hist(int64_t N, const float* R, float box, int32_t nbins, const floa
             counts[a]++;
         }
 }
+
+/* ---- the other dense pairwise kernels of the reference repo ----------------
+ * pairwise_forces(positions, masses), nbody_bh_merger_sim_single-host_workload.py NBODY:54-67:
+ *   for i, for j != i (in order): r_vec = pos[j] - pos[i]; r = ||r_vec||;
+ *   acc[i] += where(r >= 1e-6, G * m[j] / r**3, 0) * r_vec          (fp32, r**3 = r*r*r)            */
+void orc_gravity_nbody(int64_t n, const float* pos, const float* mass, float G, float* acc) {
+    for (int64_t i = 0; i < n; ++i) {
+        float ax = 0.0f, ay = 0.0f;
+        for (int64_t j = 0; j < n; ++j) {
+            if (j == i) continue;
+            float dx = pos[2 * j] - pos[2 * i], dy = pos[2 * j + 1] - pos[2 * i + 1];
+            float r = sqrtf(dx * dx + dy * dy);
+            float mag = (r >= 1.0e-6f) ? (G * mass[j]) / ((r * r) * r) : 0.0f;
+            ax = ax + mag * dx;
+            ay = ay + mag * dy;
+        }
+        acc[2 * i] = ax; acc[2 * i + 1] = ay;
+    }
+}
+/* gravity term of acceleration(pos, vel, masses, charges), three_particles_em_nonuni EM3:25-38:
+ *   r_diff = pos[j] - pos[i]; r2 = sum(r_diff^2) + eye; r2 = where(r2 < 1e-12, 1e-12, r2);
+ *   acc[i] = sum_j G * m[j] * r_diff * r2**(-1.5)                                                   */
+void orc_gravity_em3(int64_t n, const float* pos, const float* mass, float G, float* acc) {
+    for (int64_t i = 0; i < n; ++i) {
+        float ax = 0.0f, ay = 0.0f;
+        for (int64_t j = 0; j < n; ++j) {
+            float dx = pos[2 * j] - pos[2 * i], dy = pos[2 * j + 1] - pos[2 * i + 1];
+            float r2 = dx * dx + dy * dy + (i == j ? 1.0f : 0.0f);
+            if (r2 < 1.0e-12f) r2 = 1.0e-12f;
+            float inv3 = powf(r2, -1.5f);
+            ax = ax + ((G * mass[j]) * dx) * inv3;
+            ay = ay + ((G * mass[j]) * dy) * inv3;
+        }
+        acc[2 * i] = ax; acc[2 * i + 1] = ay;
+    }
+}

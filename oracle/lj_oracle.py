@@ -243,6 +243,8 @@ def c_lib():
                                          ctypes.c_float, ctypes.c_float, f32p, f64p]
         lib.orc_gr_hist.argtypes = [ctypes.c_int64, f32p, ctypes.c_float, ctypes.c_int32, f32p,
                                     i64p]
+        lib.orc_gravity_nbody.argtypes = [ctypes.c_int64, f32p, f32p, ctypes.c_float, f32p]
+        lib.orc_gravity_em3.argtypes = [ctypes.c_int64, f32p, f32p, ctypes.c_float, f32p]
         _C.lib = lib
     return _C.lib
 
@@ -329,3 +331,46 @@ def c_gr_hist(R, box, nbins, r_max):
                         edges.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
                         counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
     return counts
+
+
+# --------------------------------------------------------------------------- gravity pair laws (8f rank 4)
+def c_gravity(pos, mass, G, law="nbody"):
+    """C restatement of pairwise_forces (NBODY:54-67, law="nbody") / the gravity term of acceleration
+    (EM3:25-38, law="em3").  Returns acc (n,2) float32."""
+    pos, pp = _f32(pos)
+    mass = np.ascontiguousarray(mass, dtype=np.float32)
+    acc = np.empty_like(pos)
+    f32p = ctypes.POINTER(ctypes.c_float)
+    fn = c_lib().orc_gravity_nbody if law == "nbody" else c_lib().orc_gravity_em3
+    fn(pos.shape[0], pp, mass.ctypes.data_as(f32p), float(G), acc.ctypes.data_as(f32p))
+    return acc
+
+
+def gravity_nbody_loops(pos, mass, G):
+    """pairwise_forces exactly as written (NBODY:54-67): Python double loop, fp32 numpy scalars."""
+    pos = np.asarray(pos, dtype=np.float32)
+    mass = np.asarray(mass, dtype=np.float32)
+    G = np.float32(G)
+    n = len(pos)
+    acc = np.zeros_like(pos)
+    for i in range(n):
+        for j in range(n):
+            if i == j:
+                continue
+            r_vec = pos[j] - pos[i]
+            r_norm = np.sqrt(np.sum(r_vec * r_vec, dtype=np.float32), dtype=np.float32)
+            acc_mag = (G * mass[j] / (r_norm * r_norm * r_norm)) if r_norm >= np.float32(1e-6) else np.float32(0.0)
+            acc[i] = acc[i] + acc_mag * r_vec
+    return acc
+
+
+def gravity_em3_broadcast(pos, mass, G):
+    """Gravity term of acceleration() as written (EM3:25-38): broadcast N x N x 2 arrays, fp32."""
+    pos = np.asarray(pos, dtype=np.float32)
+    mass = np.asarray(mass, dtype=np.float32)
+    r_diff = pos[None, :, :] - pos[:, None, :]
+    r2 = np.sum(r_diff ** 2, axis=-1, dtype=np.float32) + np.eye(len(pos), dtype=np.float32)
+    r2 = np.where(r2 < np.float32(1e-12), np.float32(1e-12), r2)
+    inv3 = r2 ** np.float32(-1.5)
+    pairs = np.float32(G) * mass[None, :, None] * r_diff * inv3[..., None]
+    return np.sum(pairs, axis=1, dtype=np.float32)

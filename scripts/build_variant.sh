@@ -8,7 +8,7 @@ NAME=$1; shift
 OUT=$ROOT/variants/$NAME
 mkdir -p "$OUT"
 CSRC=$ROOT/jax_tpus_benchmark_physics_simulation_b200/csrc
-for f in api allpairs cells dist probe; do
+for f in api allpairs cells dist pairlaw probe; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-O2 "$@" \
        -c "$CSRC/$f.cu" -o "$OUT/$f.o" &
 done
