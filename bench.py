@@ -315,6 +315,15 @@ def parity_check(env, wl, sim, R, V, box, sharded):
         rebuilds = (sim.last_rebuilds(), one.last_rebuilds()) if path == "cells" else None
         ok_s = (ferr < 2e-6 and abs(pe - pe1) <= 2e-6 * abs(pe1) and derr < ptol and terr < ptol
                 and eerr < 2e-6 and (rebuilds is None or rebuilds[0] == rebuilds[1]))
+        # the block-distributed convention (ljmd_run_blocked: every rank passes / receives only its index block)
+        lo, hi = sim.block_range()
+        Rb, Vb = sim.run_blocked((R[lo:hi], V[lo:hi]), steps)
+        db = np.abs(Rb.numpy() - Ro.numpy()[lo:hi]); db = np.minimum(db, float(box) - db)
+        blk_err = float(db.max())
+        vb_err = float(np.abs(Vb.numpy() - Vo.numpy()[lo:hi]).max())
+        ok_s = ok_s and blk_err < ptol and vb_err < max(1e-3, 20.0 * ptol)
+        out["blocked_io_vs_single"] = {"ok": bool(blk_err < ptol and vb_err < max(1e-3, 20.0 * ptol)),
+                                       "max_dR": blk_err, "max_dV": vb_err, "block": [int(lo), int(hi)]}
         out["sharded_vs_single"] = {"ok": bool(ok_s), "force_err": ferr, "pe_rel": abs(pe - pe1) / abs(pe1),
                                     "steps": steps, "max_dR": derr, "traj_err": terr, "pos_tol": ptol,
                                     "energy_rel": eerr, "rebuilds": rebuilds}
@@ -372,8 +381,12 @@ def measure(env, wl_name, args, steps, warmup, cpu_steps=0, check=True):
 
     Rd = torch.from_numpy(R).cuda()
     Vd = torch.from_numpy(V).cuda()
-    Rh = torch.from_numpy(R).pin_memory()
-    Vh = torch.from_numpy(V).pin_memory()
+    # e2e buffers: a sharded run moves block-distributed state (every rank its own index block of the arrays,
+    # LJSimulation.run_blocked), a single-GPU / replica run the whole arrays
+    blocked_io = sharded and N % world == 0
+    lo, hi = sim.block_range() if blocked_io else (0, N)
+    Rh = torch.from_numpy(R[lo:hi].copy()).pin_memory()
+    Vh = torch.from_numpy(V[lo:hi].copy()).pin_memory()
     Rh_out = torch.empty_like(Rh).pin_memory()
     Vh_out = torch.empty_like(Vh).pin_memory()
     E_out = torch.empty((1, 2), dtype=torch.float32).pin_memory()
@@ -409,7 +422,10 @@ def measure(env, wl_name, args, steps, warmup, cpu_steps=0, check=True):
     for k in range(steps):
         Rk = Rh.to("cuda", non_blocking=True)
         Vk = Vh.to("cuda", non_blocking=True)
-        (Ro, Vo), _ = sim.run((Rk, Vk), md_steps, energy_every=md_steps)
+        if blocked_io:
+            Ro, Vo = sim.run_blocked((Rk, Vk), md_steps, energy_every=md_steps)
+        else:
+            (Ro, Vo), _ = sim.run((Rk, Vk), md_steps, energy_every=md_steps)
         Rh_out.copy_(Ro.tensor, non_blocking=True)
         Vh_out.copy_(Vo.tensor, non_blocking=True)
         E_out.copy_(sim.last_energies.tensor, non_blocking=True)
@@ -417,8 +433,9 @@ def measure(env, wl_name, args, steps, warmup, cpu_steps=0, check=True):
     env.barrier()
     t_e2e = env.max_over_ranks(time.perf_counter() - e0)
     e2e_value = total_particles * md_steps * steps / t_e2e
-    h2d = Rh.numel() * 4 + Vh.numel() * 4
-    d2h = Rh_out.numel() * 4 + Vh_out.numel() * 4 + E_out.numel() * 4
+    nio = world if blocked_io else 1                 # whole-job bytes: every rank moves its own block
+    h2d = (Rh.numel() * 4 + Vh.numel() * 4) * nio
+    d2h = (Rh_out.numel() * 4 + Vh_out.numel() * 4) * nio + E_out.numel() * 4
 
     # one more run on EVERY rank (a sharded run is collective) for the per-launch kernel time
     env.barrier()
@@ -434,7 +451,9 @@ def measure(env, wl_name, args, steps, warmup, cpu_steps=0, check=True):
            "ms_per_step": 1e3 * t_dev / steps, "steps": steps, "warmup": warmup,
            "pair_interactions_per_s": (value * (N - 1)) if wl["path"] == "allpairs" else None,
            "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d,
-                   "d2h_bytes_per_step": d2h},
+                   "d2h_bytes_per_step": d2h,
+                   "io": "block-distributed (run_blocked): bytes summed over the ranks" if blocked_io
+                         else "whole arrays per call"},
            "gpu_launches": int(launches), "wall_s": wall, "clocks": clocks, "parity_check": parity}
     if rank != 0:
         sim.close()

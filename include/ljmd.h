@@ -158,6 +158,16 @@ int ljmd_get_unique_id(void* id128);
 int ljmd_create_dist(ljmd_t** out, const ljmd_params* p, const void* nccl_unique_id,
                      int32_t rank, int32_t nranks);
 
+/* Block-distributed state for multi-GPU handles (the replicated convention above makes every rank
+ * move the whole (N,2) arrays through PCIe and NVLink on every call): rank p passes and receives only
+ * the particles of its INDEX block [p N/P, (p+1) N/P) - pointers to (N/P,2) device arrays; N must be
+ * divisible by P.  Same physics as ljmd_run without trajectory sampling and thermostat.  Inside, the
+ * blocks are all-gathered once (NCCL over NVLink) and every owner stores the final state of its
+ * particles straight into the staging block of the rank that holds their index (in-kernel peer stores
+ * on the cell path).  With one rank this is ljmd_run.                                              */
+int ljmd_run_blocked(ljmd_t* h, const float* R_blk, const float* V_blk, float* R_blk_out, float* V_blk_out,
+                     int64_t nsteps, int64_t energy_every, float* ke_pe);
+
 /* ---- run status -------------------------------------------------------------------- */
 /* The calls above only ENQUEUE work (JAX-style async dispatch), so conditions that a persistent
  * kernel detects on the device cannot come back through their return value: a Verlet list or a

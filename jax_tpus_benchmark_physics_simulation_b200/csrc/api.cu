@@ -115,6 +115,7 @@ void ljmd_destroy(ljmd_t* h) {
     ap_destroy(h);
     cells_destroy(h);
     dist_destroy(h);
+    for (int k = 0; k < 4; ++k) cudaFree(h->blk_full[k]);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
@@ -170,6 +171,41 @@ int ljmd_run(ljmd_t* h, const float* R_in, const float* V_in, float* R_out, floa
     rc.thermo_kT = (thermostat_kT > 0.0f && thermostat_every > 0) ? thermostat_kT : 0.0f;
     rc.thermo_every = rc.thermo_kT > 0.0f ? thermostat_every : 0;
     return run_dispatch(h, R_in, V_in, R_out, V_out, nullptr, nullptr, rc);
+}
+
+int ljmd_run_blocked(ljmd_t* h, const float* R_blk, const float* V_blk, float* R_blk_out, float* V_blk_out,
+                     int64_t nsteps, int64_t energy_every, float* ke_pe) {
+    if (!h || !R_blk || !V_blk || !R_blk_out || !V_blk_out) { set_error("null argument"); return LJMD_E_INVALID; }
+    if (nsteps < 1 || energy_every < 0) { set_error("ljmd_run_blocked: nsteps >= 1"); return LJMD_E_INVALID; }
+    if (h->nranks == 1)      // one rank: its block is everything
+        return ljmd_run(h, R_blk, V_blk, R_blk_out, V_blk_out, nsteps, 0, nullptr, energy_every, ke_pe, 0.0f, 0);
+    const long long N = h->p.N;
+    if (N % h->nranks != 0) { set_error("block-distributed I/O needs N divisible by the GPU count"); return LJMD_E_INVALID; }
+    LJ_CUDA(cudaSetDevice(h->p.device));
+    RunCtl rc{};
+    rc.nsteps = nsteps;
+    rc.energy_every = (ke_pe && energy_every > 0) ? energy_every : 0;
+    rc.ke_pe = ke_pe;
+    rc.blocked = 1;
+    const float2* R = reinterpret_cast<const float2*>(R_blk);
+    const float2* V = reinterpret_cast<const float2*>(V_blk);
+    if (h->path != LJMD_PATH_ALLPAIRS)
+        return cells_run(h, R, V, reinterpret_cast<float2*>(R_blk_out), reinterpret_cast<float2*>(V_blk_out),
+                         nullptr, nullptr, rc);
+    // all-pairs: the state is at most 1 MiB, so the blocks are simply all-gathered (NCCL over NVLink), the
+    // replicated run is used as it is, and the rank's block is sliced out of its result
+    const size_t blk = sizeof(float2) * (size_t)(N / h->nranks);
+    for (int k = 0; k < 4; ++k)
+        if (!h->blk_full[k]) LJ_CUDA(cudaMalloc(&h->blk_full[k], sizeof(float2) * (size_t)N));
+    int r = dist_allgather_from(h, R, h->blk_full[0], blk);
+    if (!r) r = dist_allgather_from(h, V, h->blk_full[1], blk);
+    if (r) return r;
+    rc.blocked = 0;
+    r = ap_run(h, h->blk_full[0], h->blk_full[1], h->blk_full[2], h->blk_full[3], nullptr, nullptr, rc);
+    if (r) return r;
+    LJ_CUDA(cudaMemcpyAsync(R_blk_out, reinterpret_cast<char*>(h->blk_full[2]) + blk * h->rank, blk, cudaMemcpyDeviceToDevice, h->stream));
+    LJ_CUDA(cudaMemcpyAsync(V_blk_out, reinterpret_cast<char*>(h->blk_full[3]) + blk * h->rank, blk, cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
 }
 
 int ljmd_gr_hist(ljmd_t* h, const float* R_hist, int64_t S, int32_t nbins, const float* edges,

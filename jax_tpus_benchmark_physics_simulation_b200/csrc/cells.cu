@@ -136,6 +136,11 @@ struct CellsArgs {
     long long spin_limit;           // clocks a spin wait may last (0 = unlimited)
     RunCtl rc;
     float2 *R_out, *V_out, *F_out;
+    // block-distributed output (ljmd_run_blocked): the owner of a particle stores its final state straight
+    // into the staging block of the rank that owns its ORIGINAL index (NVLink peer store)
+    int     blk;                    // particles per index block (0 = replicated output)
+    float2* peer_stageR[LJMD_MAX_RANKS];
+    float2* peer_stageV[LJMD_MAX_RANKS];
     float*  pe_out;
     int*    count_out;              // count mode: neighbour counts in original order
     int     mode;                   // 0 = run, 1 = build + count only
@@ -1012,9 +1017,15 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
                 V[i] = v;
                 a.Fs[i] = make_float2(Fx, Fy);
             } else if (final) {
-                if (a.R_out) a.R_out[o] = ri;
-                if (a.V_out) a.V_out[o] = v;
-                if (a.F_out) a.F_out[o] = make_float2(Fx, Fy);
+                if (a.blk > 0) {
+                    const int qd = o / a.blk, oo = o - qd * a.blk;
+                    a.peer_stageR[qd][oo] = ri;
+                    a.peer_stageV[qd][oo] = v;
+                } else {
+                    if (a.R_out) a.R_out[o] = ri;
+                    if (a.V_out) a.V_out[o] = v;
+                    if (a.F_out) a.F_out[o] = make_float2(Fx, Fy);
+                }
             } else {
                 v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt);                           // MD:70
                 V[i] = v;
@@ -1227,8 +1238,10 @@ cells_persistent_kernel(const CellsArgs a) {
         if (__syncthreads_or(moved) && tid == 0) __stcg(a.state + (a.P > 1 ? ST_LMOVED : ST_FLAG), (int)(s + 2));
         if (!final) ctx.pr ^= 1;
         CL_PROF(0);
+        if (final && a.blk > 0) __threadfence_system();      // the staged outputs live on peer GPUs
         CL_BARRIER();
         CL_PROF(1);
+        if (a.P > 1 && final && a.blk > 0) (void)peer_sync(a, ctx, false);   // every rank's outputs have landed
         if (a.P > 1 && !final) {
             // one NVLink round trip per step: every rank's halo pushes have landed once all arrival
             // words carry this epoch; the words also carry "one of my particles left its skin/2 ball",
@@ -1287,6 +1300,8 @@ struct Cells {
     // words, mailbox -- at the same offsets on every rank
     void* shared = nullptr;
     size_t off_R[2] = {}, off_V[2] = {}, off_O[2] = {}, off_cc = 0, off_flags = 0, off_mail = 0;
+    size_t off_stage[2] = {};       // block-distributed output staging (R, V), P > 1 only
+    float2 *Rfull = nullptr, *Vfull = nullptr;   // all-gathered input of ljmd_run_blocked (allocated on first use)
     char* peer_base[LJMD_MAX_RANKS] = {};
     float2 *Rb = nullptr, *Fs = nullptr;
     int *key = nullptr, *rank = nullptr, *tmpk = nullptr, *tmpo = nullptr, *tmpc = nullptr,
@@ -1373,6 +1388,8 @@ int cells_create(ljmd_handle* h) {
         cl->off_cc = off;    off += up(sizeof(int) * (size_t)cl->ncells_max);
         cl->off_flags = off; off += up(sizeof(unsigned) * 2 * LJMD_MAX_RANKS);
         cl->off_mail = off;  off += up(sizeof(int) * MB_WORDS);
+        if (P > 1 && N % P == 0)
+            for (int k = 0; k < 2; ++k) { cl->off_stage[k] = off; off += up(sizeof(float2) * (size_t)(N / P)); }
         const size_t bytes = std::max<size_t>((off + (2u << 20) - 1) / (2u << 20) * (2u << 20), 4u << 20);
         LJ_CUDA(cudaMalloc(&cl->shared, bytes));
         LJ_CUDA(cudaMemset(cl->shared, 0, bytes));
@@ -1411,6 +1428,7 @@ void cells_destroy(ljmd_handle* h) {
     Cells* cl = h->cells;
     if (!cl) return;
     cudaFree(cl->shared);
+    cudaFree(cl->Rfull); cudaFree(cl->Vfull);
     cudaFree(cl->Rb); cudaFree(cl->Fs); cudaFree(cl->key); cudaFree(cl->rank);
     cudaFree(cl->tmpk); cudaFree(cl->tmpo); cudaFree(cl->tmpc); cudaFree(cl->meta);
     cudaFree(cl->ent); cudaFree(cl->wplan); cudaFree(cl->nb4);
@@ -1446,6 +1464,8 @@ static void fill_args(ljmd_handle* h, CellsArgs& a) {
         a.peer_cc[q] = reinterpret_cast<int*>(base + cl->off_cc);
         a.peer_flags[q] = reinterpret_cast<unsigned*>(base + cl->off_flags);
         a.peer_mail[q] = reinterpret_cast<int*>(base + cl->off_mail);
+        a.peer_stageR[q] = reinterpret_cast<float2*>(base + cl->off_stage[0]);
+        a.peer_stageV[q] = reinterpret_cast<float2*>(base + cl->off_stage[1]);
     }
     for (int k = 0; k < 2; ++k) { a.R[k] = a.peerR[k][h->rank]; a.V[k] = a.peerV[k][h->rank]; a.orig[k] = a.peerO[k][h->rank]; }
     a.cell_count = a.peer_cc[h->rank];
@@ -1475,19 +1495,38 @@ int cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_
     const long long N = h->p.N;
     const int P = cl->P;
     cudaStream_t st = h->stream;
+    const bool blocked = P > 1 && rc.blocked != 0;
+    if (blocked) {
+        if (N % P != 0 || cl->off_stage[1] == 0) { set_error("block-distributed I/O needs N divisible by the GPU count"); return LJMD_E_INVALID; }
+        if (rc.nsteps <= 0 || rc.sample_every > 0 || F_out || !R_out || !V_out) {
+            set_error("block-distributed I/O: a run of >= 1 step without trajectory sampling");
+            return LJMD_E_UNSUPPORTED;
+        }
+        // the caller's index blocks -> the full arrays the slab filter of the load phase reads
+        if (!cl->Rfull) {
+            LJ_CUDA(cudaMalloc(&cl->Rfull, sizeof(float2) * N));
+            LJ_CUDA(cudaMalloc(&cl->Vfull, sizeof(float2) * N));
+        }
+        int r = dist_allgather_from(h, R_in, cl->Rfull, sizeof(float2) * (size_t)(N / P));
+        if (!r) r = dist_allgather_from(h, V_in, cl->Vfull, sizeof(float2) * (size_t)(N / P));
+        if (r) return r;
+        R_in = cl->Rfull; V_in = cl->Vfull;
+    }
     if (P > 1) {
         if (rc.thermo_every > 0 && rc.thermo_kT > 0.0f) {
             set_error("the thermostat is not available on the multi-GPU cell-list path");
             return LJMD_E_UNSUPPORTED;
         }
-        if ((R_out && R_out == R_in) || (V_out && V_out == V_in)) {
+        if (!blocked && ((R_out && R_out == R_in) || (V_out && V_out == V_in))) {
             set_error("multi-GPU cell-list path: outputs must not alias the inputs");
             return LJMD_E_UNSUPPORTED;
         }
         // every rank writes only the particles it owns; the replicated result is the sum
-        if (R_out) LJ_CUDA(cudaMemsetAsync(R_out, 0, sizeof(float2) * N, st));
-        if (V_out) LJ_CUDA(cudaMemsetAsync(V_out, 0, sizeof(float2) * N, st));
-        if (F_out) LJ_CUDA(cudaMemsetAsync(F_out, 0, sizeof(float2) * N, st));
+        if (!blocked) {
+            if (R_out) LJ_CUDA(cudaMemsetAsync(R_out, 0, sizeof(float2) * N, st));
+            if (V_out) LJ_CUDA(cudaMemsetAsync(V_out, 0, sizeof(float2) * N, st));
+            if (F_out) LJ_CUDA(cudaMemsetAsync(F_out, 0, sizeof(float2) * N, st));
+        }
     }
     if (rc.nsteps > 0 && rc.traj && rc.S > 0)
         LJ_CUDA(cudaMemsetAsync(rc.traj, 0, sizeof(float2) * N * rc.S, st));      // MD:89
@@ -1499,6 +1538,7 @@ int cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_
     a.R_in = R_in; a.V_in = V_in;
     a.rc = rc;
     a.R_out = R_out; a.V_out = V_out; a.F_out = F_out; a.pe_out = pe_out;
+    a.blk = blocked ? (int)(N / P) : 0;
     a.mode = 0;
     // bound one launch to roughly half a second (conservative 2e10 particle-steps/s)
     long long chunk = std::max<long long>(1, (long long)(1.0e10 / (double)N));
@@ -1517,8 +1557,15 @@ int cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_
     if (P > 1) {
         // replicated out (NCCL over NVLink, once per call): owner-written entries + zeros elsewhere
         int r = 0;
-        if (R_out && (r = dist_allreduce_f32(h, reinterpret_cast<float*>(R_out), (size_t)2 * N))) return r;
-        if (V_out && (r = dist_allreduce_f32(h, reinterpret_cast<float*>(V_out), (size_t)2 * N))) return r;
+        if (blocked) {
+            // the kernel's last cross-GPU sync guarantees that every owner's stores into this rank's staging
+            // block have landed; the next call's entry barrier keeps the peers from overwriting it early
+            char* base = reinterpret_cast<char*>(cl->shared);
+            LJ_CUDA(cudaMemcpyAsync(R_out, base + cl->off_stage[0], sizeof(float2) * (size_t)(N / P), cudaMemcpyDeviceToDevice, st));
+            LJ_CUDA(cudaMemcpyAsync(V_out, base + cl->off_stage[1], sizeof(float2) * (size_t)(N / P), cudaMemcpyDeviceToDevice, st));
+        }
+        if (!blocked && R_out && (r = dist_allreduce_f32(h, reinterpret_cast<float*>(R_out), (size_t)2 * N))) return r;
+        if (!blocked && V_out && (r = dist_allreduce_f32(h, reinterpret_cast<float*>(V_out), (size_t)2 * N))) return r;
         if (F_out && (r = dist_allreduce_f32(h, reinterpret_cast<float*>(F_out), (size_t)2 * N))) return r;
         if (rc.traj && rc.S > 0 && (r = dist_allreduce_f32(h, reinterpret_cast<float*>(rc.traj), (size_t)2 * N * rc.S))) return r;
         if (pe_out && (r = dist_allreduce_f32(h, pe_out, 1))) return r;

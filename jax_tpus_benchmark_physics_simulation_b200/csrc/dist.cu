@@ -148,6 +148,12 @@ int dist_allgather(ljmd_handle* h, void* buf, size_t bytes_per_rank) {
     return 0;
 }
 
+int dist_allgather_from(ljmd_handle* h, const void* send, void* recv, size_t bytes_per_rank) {
+    Dist* d = h->dist;
+    LJ_NCCL(g_nccl.AllGather(send, recv, bytes_per_rank, ncclInt8, d->comm, h->stream));
+    return 0;
+}
+
 int dist_allreduce_f32(ljmd_handle* h, float* buf, size_t n) {
     Dist* d = h->dist;
     LJ_NCCL(g_nccl.AllReduce(buf, buf, n, ncclFloat32, ncclSum, d->comm, h->stream));

@@ -56,6 +56,8 @@ struct RunCtl {
     float     thermo_kT;
     float2*   traj;           // (S,N,2)
     float*    ke_pe;          // (ceil(nsteps/energy_every),2)
+    int       blocked;        // multi-GPU: R/V pointers address the rank's INDEX BLOCK [rank N/P, (rank+1) N/P)
+                              // only (ljmd_run_blocked) instead of the full replicated arrays
 };
 
 struct AllPairs;   // allpairs.cu
@@ -78,6 +80,7 @@ struct ljmd_handle {
     long long        launches;
     int              rank, nranks;
     long long        spin_limit;  // clocks a device-side spin wait may last (0 = unlimited)
+    float2*          blk_full[4]; // all-pairs ljmd_run_blocked: replicated in / out arrays (allocated on first use)
 };
 
 namespace ljmd {
@@ -112,6 +115,7 @@ int  dist_init(ljmd_handle* h, const void* nccl_unique_id);
 void dist_destroy(ljmd_handle* h);
 int  dist_share(ljmd_handle* h, void* local_base, void** peer_bases /*[nranks]*/);
 int  dist_allgather(ljmd_handle* h, void* buf, size_t bytes_per_rank);   // in place, slab `rank`
+int  dist_allgather_from(ljmd_handle* h, const void* send, void* recv, size_t bytes_per_rank);
 int  dist_allreduce_f32(ljmd_handle* h, float* buf, size_t n);
 int  dist_barrier(ljmd_handle* h);                      // cross-rank barrier in stream order
 

@@ -123,6 +123,7 @@ class LJSimulation:
         self._stream = torch.cuda.current_stream(self.device)
         p.stream = ctypes.c_void_p(self._stream.cuda_stream)
         self._h = ctypes.c_void_p()
+        self._dist_rank = (0, 1) if dist is None else (int(dist[1]), int(dist[2]))
         if dist is None:
             _lib.check(self.lib.ljmd_create(ctypes.byref(self._h), ctypes.byref(p)), "ljmd_create")
         else:
@@ -245,6 +246,29 @@ class LJSimulation:
     def run(self, state, nsteps: int, sample_every: int = 0, energy_every: int = 0):
         """nsteps velocity-Verlet steps in one device dispatch; returns (state, traj)."""
         return self._run(state, int(nsteps), int(sample_every), int(energy_every))
+
+    def block_range(self) -> Tuple[int, int]:
+        """Index block [lo, hi) of this rank in the block-distributed convention of run_blocked."""
+        rank, nranks = self._dist_rank
+        return slab_range(self.N, rank, nranks)
+
+    def run_blocked(self, state_block, nsteps: int, energy_every: int = 0):
+        """nsteps steps with BLOCK-DISTRIBUTED state (multi-GPU handles; ljmd_run_blocked): this rank
+        passes and receives only the particles of its index block ``block_range()`` as (N/P, 2)
+        arrays, so a step's host<->device traffic is 1/P of the state.  Returns (R_block, V_block)."""
+        lo, hi = self.block_range()
+        R = self._dev(state_block[0], (hi - lo, 2))
+        V = self._dev(state_block[1], (hi - lo, 2))
+        R_out, V_out = torch.empty_like(R), torch.empty_like(V)
+        ne = -(-nsteps // energy_every) if energy_every > 0 else 0
+        ke_pe = torch.zeros((ne, 2), dtype=torch.float32, device=self.device) if ne else None
+        self._check_stream()
+        _lib.check(self.lib.ljmd_run_blocked(
+            self._h, R.data_ptr(), V.data_ptr(), R_out.data_ptr(), V_out.data_ptr(), int(nsteps),
+            energy_every if ne else 0, ke_pe.data_ptr() if ne else None), "ljmd_run_blocked")
+        self._after()
+        self.last_energies = self._arr(ke_pe) if ne else None
+        return self._arr(R_out), self._arr(V_out)
 
     def equilibrate_fn(self, initial_state):
         """fori_loop(0, equilibration_steps, verlet_step) — one dispatch, NVE (MD:77-83)."""

@@ -78,3 +78,19 @@ def test_sharded_cells_matches_single_gpu():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("-> OK") == 2
+
+
+def test_run_blocked_single_rank_is_run():
+    """ljmd_run_blocked with one rank: the block is everything, the result is ljmd_run's bit for bit."""
+    import numpy as np
+    from jax_tpus_benchmark_physics_simulation_b200 import lattice_jitter
+    from jax_tpus_benchmark_physics_simulation_b200.md import LJSimulation
+    for path, N in (("allpairs", 1024), ("cells", 16384)):
+        R, V, box = lattice_jitter(N, seed=1)
+        sim = LJSimulation(N, rc=2.5, dt=0.005, path=path)
+        assert sim.block_range() == (0, N)
+        (R1, V1), _ = sim.run((R, V), 25, energy_every=5)
+        e1 = sim.last_energies.numpy()
+        R2, V2 = sim.run_blocked((R, V), 25, energy_every=5)
+        assert np.array_equal(R1.numpy(), R2.numpy()) and np.array_equal(V1.numpy(), V2.numpy())
+        assert np.array_equal(e1, sim.last_energies.numpy())
