@@ -74,6 +74,14 @@ constexpr int CL_WARP_SMEM = 2 * CL_WINBYTES + 2 * CL_SWBYTES;   // bytes per wa
 #ifndef CL_UNROLL
 #define CL_UNROLL 2
 #endif
+// how a unit's windows and list words reach shared memory: 0 = bulk copies (cp.async.bulk / UBLKCP issued by
+// four lanes, completion on an mbarrier), 1 = per-lane 16-byte cp.async (LDGSTS.128, commit / wait groups)
+#ifndef CL_COPY
+#define CL_COPY 0
+#endif
+#ifndef CL_DEPTH3
+#define CL_DEPTH3 0     // 1 = a warp holds three units in flight (the schedule before the two-unit pipeline)
+#endif
 constexpr int CL_WORD_UNROLL = CL_UNROLL;                   // list words per trip of the pair loop
 constexpr int CL_UNITWORDS = CL_NW * 32;                    // list words of one 32-slot unit in nb4
 static_assert(CL_WINBYTES + 32 * CL_BROW <= CL_WARP_SMEM, "byte rows must fit behind window buffer 0");
@@ -797,6 +805,13 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
 //  the async-proxy reads of later bulk copies by one fence.proxy.async.global on each side of every grid
 //  barrier and after every cross-GPU sync: CL_BARRIER, peer_sync)
 
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ float2 lds64(unsigned addr) {
     float2 v;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
@@ -914,6 +929,29 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
     const char* Lbytes = reinterpret_cast<const char*>(a.nb4);
     const unsigned my_dst = wp.base + (lane < 3 ? lane * (CL_WIN * 8) : 2 * CL_WINBYTES);   // + buf * stride
     const unsigned my_stride = lane < 3 ? CL_WINBYTES : CL_SWBYTES;
+#if CL_COPY == 1
+    const unsigned l16 = lane * 16;
+    auto issue = [&](int u, const int4& p, int buf) {
+        if (u < u_hi && p.w < 0) {
+            const unsigned pw = (unsigned)p.w;
+            const unsigned win = wp.base + buf * CL_WINBYTES + l16, sw = wp.base + 2 * CL_WINBYTES + buf * CL_SWBYTES + l16;
+            const int wsk[3] = {p.x, p.y, p.z};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {           // a window is at most 84 slots = 672 bytes: chunks l16 and l16 + 512
+                const unsigned bytes = ((pw >> (8 * k)) & 0xffu) * 8u;
+                const char* src = Rbytes + (size_t)wsk[k] * 8 + l16;
+                if (l16 < bytes) cp_async16(win + k * (CL_WIN * 8), src);
+                if (l16 + 512 < bytes) cp_async16(win + k * (CL_WIN * 8) + 512, src + 512);
+            }
+            const unsigned wbytes = min((pw >> 24) & 0x7fu, (unsigned)CL_NWS) * 128u;
+            const char* src = Lbytes + (size_t)u * (CL_UNITWORDS * 4) + l16;
+#pragma unroll
+            for (int c = 0; c < CL_SWBYTES; c += 512)
+                if (l16 + c < wbytes) cp_async16(sw + c, src + c);
+        }
+        cp_async_commit();
+    };
+#else
     auto issue = [&](int u, const int4& p, int buf) {
         if (u < u_hi && p.w < 0) {
             const unsigned pw = (unsigned)p.w;
@@ -937,6 +975,7 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
             }
         }
     };
+#endif
     // Schedule: the first ~60 % of the units statically interleaved (no traffic), the rest drawn one by
     // one from a per-step counter: warps that met several slow (edge) units take fewer of the tail.
     const int rounds0 = (int)(a.static_frac * (float)((u_hi - u_lo) / W));
@@ -954,19 +993,29 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
     auto fix = [&](int raw, int j) -> int { return j < rounds0 ? raw + u_lo : dyn_lo + ctx.q + ctx.nq * raw; };
     const int4 z4 = make_int4(0, 0, 0, 0);
     int u = fix(__shfl_sync(0xffffffffu, grab(0), 0), 0), un = fix(__shfl_sync(0xffffffffu, grab(1), 0), 1);
-    int g = grab(2);                                      // drawn now, broadcast one unit later
     int4 p = z4, q = z4;
     if (u < u_hi) p = a.wplan[u];
     if (un < u_hi) q = a.wplan[un];
     issue(u, p, 0);
+#if CL_DEPTH3
+    int g3 = grab(2);
+#endif
 
     for (int k = 0; u < u_hi; ++k) {
         const int buf = k & 1;
         issue(un, q, buf ^ 1);                            // next unit's windows + words
-        const int unn = fix(__shfl_sync(0xffffffffu, g, 0), k + 2);
-        g = grab(k + 3);
+#if CL_DEPTH3
+        // (older schedule: a warp holds three units - the draw is made a whole unit before its plan is read)
+        const int unn = fix(__shfl_sync(0xffffffffu, g3, 0), k + 2);
+        g3 = grab(k + 3);
         int4 r = z4;
         if (unn < u_hi) r = a.wplan[unn];                 // consumed next iteration
+#else
+        // the unit after next is drawn now; its number is broadcast and its plan requested after the pair
+        // loop (the atomic's round trip hides behind it, the plan's behind the epilogue), so a warp holds
+        // TWO units when the queue runs dry: a shorter tail at the step barrier
+        const int g = grab(k + 2);
+#endif
         const int  i    = u * 32 + lane;
         const bool live = (i >= ctx.own_s) & (i < ctx.own_e);
         // epilogue operands requested now, consumed after the pair loop
@@ -974,11 +1023,17 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
         if (live && (PLAIN || rc.nsteps > 0)) { v = V[i]; rb = a.Rb[i]; }
         float2 ri = make_float2(0.0f, 0.0f);
         float Fx = 0.0f, Fy = 0.0f, pe = 0.0f, ke = 0.0f;
+#if CL_COPY == 1
+        cp_async_wait<1>();                               // this unit's copy group has landed
+        __syncwarp();
+#endif
         if (p.w < 0) {
+#if CL_COPY == 0
             // this unit's copies have landed when the buffer's mbarrier completes its phase
             const unsigned bar = wp.bar + buf * 8, par = (wp.phase >> buf) & 1u;
             if (!mbar_try_wait(bar, par)) mbar_wait_slow(a, bar, par);
             wp.phase ^= 1u << buf;
+#endif
             const unsigned win = wp.base + buf * CL_WINBYTES;
             CL_ASSERT(!live || (i - p.y >= 0 && i - p.y < (int)(((unsigned)p.w >> 8) & 0xffu)));
 #ifdef LJMD_DEBUG_CHECKS
@@ -1007,6 +1062,11 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
             if (wedge) list_force<PE, true >(a, R, ii, n, ri, Fx, Fy, pe);
             else       list_force<PE, false>(a, R, ii, n, ri, Fx, Fy, pe);
         }
+#if !CL_DEPTH3
+        const int unn = fix(__shfl_sync(0xffffffffu, g, 0), k + 2);
+        int4 r = z4;
+        if (unn < u_hi) r = a.wplan[unn];                 // consumed at the top of the next iteration
+#endif
         if (live) {
             if (kick1) { v.x = kick(v.x, Fx, a.dt); v.y = kick(v.y, Fy, a.dt); }               // MD:74
             if (want_ke) ke = v.x * v.x + v.y * v.y;
@@ -1067,6 +1127,9 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
         __syncwarp();                                     // all lanes are done with `buf`
         u = un; un = unn; p = q; q = r;
     }
+#if CL_COPY == 1
+    cp_async_wait<0>();
+#endif
 }
 
 extern __shared__ __align__(16) unsigned char cells_smem[];
