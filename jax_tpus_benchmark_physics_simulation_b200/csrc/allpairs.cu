@@ -407,16 +407,23 @@ ap_persistent_kernel(const ApArgs a) {
                 volatile unsigned* f = a.peer_flags[tid] + a.rank;
                 *f = xe;
             }
-            if (tid == 0) {
-                const volatile unsigned* mine = a.peer_flags[a.rank];
-                long long t0 = clock64();
-                for (int q = 0; q < a.P; ++q) {
-                    if (q == a.rank) continue;
-                    while ((int)(mine[q] - xe) < 0) {
-                        if (a.spin_limit > 0 && clock64() - t0 > 2 * a.spin_limit) { atomicExch(a.err, 2); break; }
+            if (tid < 32) {
+                // lane q polls the word of rank q: the P - 1 words are in flight together (one round trip
+                // to L2 when they have already landed, instead of P - 1 dependent ones)
+                const bool other = (tid < a.P) && (tid != a.rank);
+                const unsigned* word = a.peer_flags[a.rank] + (other ? tid : 0);
+                const long long t0 = clock64();
+                for (;;) {
+                    bool done = true;
+                    if (other) {
+                        unsigned w;
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(w) : "l"(word) : "memory");
+                        done = (int)(w - xe) >= 0;
                     }
+                    if (__all_sync(0xffffffffu, done)) break;
+                    const bool giveup = a.spin_limit > 0 && clock64() - t0 > 2 * a.spin_limit;
+                    if (__any_sync(0xffffffffu, giveup)) { if (tid == 0) atomicExch(a.err, 2); break; }
                 }
-                __threadfence_system();
             }
             __syncthreads();
         };
