@@ -921,6 +921,9 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
         asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(wp.base + (3 * CL_WIN + (lane & 3)) * 8), "f"(1.0e9f) : "memory");
         asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(wp.base + CL_WINBYTES + (3 * CL_WIN + (lane & 3)) * 8), "f"(1.0e9f) : "memory");
     }
+    // this warp's shared memory was last written through the generic proxy (the list build's byte rows):
+    // order those writes before the bulk copies that now land in the same bytes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
 
     // copy plan of a unit: (ws0, ws1, ws2, wn0 | wn1 << 8 | wn2 << 16 | nw << 24 | staged << 31).

@@ -190,7 +190,7 @@ def test_full_size_config4_properties(oracle):
 
 
 @pytest.mark.parametrize("rho,rc,kind", [(0.8, 2.5, "uniform"), (0.05, 2.5, "uniform"), (1.1, 2.5, "soft"),
-                                           (0.8, 3.5, "soft")])
+                                           (0.8, 3.5, "soft"), (1.3, 3.0, "soft")])
 def test_non_lattice_inputs_vs_oracle(oracle, rho, rc, kind):
     """Inputs that are not lattice-like: uniform random positions (the reference's own IC style,
     MD:133: overlapping particles, |F| up to 1e30), sparse and dense systems, a longer cutoff.
@@ -215,3 +215,28 @@ def test_non_lattice_inputs_vs_oracle(oracle, rho, rc, kind):
     assert np.abs(F[fin] - Fa[fin]).max() / scale <= FORCE_TOL
     got = sim.neighbor_count(R, rc).cpu().numpy()
     assert np.array_equal(got, oracle.c_neighbor_count(R, box, rc))
+
+
+def test_long_lists_tail_words_dynamics():
+    """rho = 1.3, rc = 3.0 (+ skin 0.3): ~44 neighbours per list, more than the 40 whose index words are
+    staged in shared memory, so every unit also walks the global-memory tail of its list; 40 steps with
+    rebuilds against the all-pairs kernel on the same inputs."""
+    from jax_tpus_benchmark_physics_simulation_b200.ic import box_size
+    N, rho, rc, dt = 16384, 1.3, 3.0, 0.002
+    rng = np.random.default_rng(3)
+    box = box_size(N, rho)
+    n = int(round(np.sqrt(N))); a = float(box) / n
+    g = (np.stack(np.meshgrid(np.arange(n), np.arange(n), indexing="ij"), -1).reshape(-1, 2) + 0.5) * a
+    R = np.mod(g + rng.uniform(-0.05, 0.05, g.shape) * a, float(box)).astype(np.float32)
+    V = (2.0 * rng.standard_normal((N, 2))).astype(np.float32)
+    cells = _sim(N, rho=rho, rc=rc, dt=dt)
+    ap = _sim(N, rho=rho, rc=rc, dt=dt, path="allpairs")
+    assert float(cells.neighbor_count(R, rc + 0.3).float().mean()) > 40.0
+    (Rc, Vc), _ = cells.run((R, V), 40, energy_every=10)
+    ec = cells.last_energies.numpy()
+    (Ra, Va), _ = ap.run((R, V), 40, energy_every=10)
+    ea = ap.last_energies.numpy()
+    Rc.block_until_ready()
+    assert cells.last_rebuilds() >= 2
+    assert _pdist(Rc.numpy(), Ra.numpy(), box).max() <= 1e-4
+    assert np.abs(ec.sum(1) - ea.sum(1)).max() <= 2e-6 * np.abs(ea.sum(1)).max()
