@@ -82,6 +82,7 @@ constexpr int CL_WARP_SMEM = 2 * CL_WINBYTES + 2 * CL_SWBYTES;   // bytes per wa
 #ifndef CL_DEPTH3
 #define CL_DEPTH3 0     // 1 = a warp holds three units in flight (the schedule before the two-unit pipeline)
 #endif
+
 constexpr int CL_WORD_UNROLL = CL_UNROLL;                   // list words per trip of the pair loop
 constexpr int CL_UNITWORDS = CL_NW * 32;                    // list words of one 32-slot unit in nb4
 static_assert(CL_WINBYTES + 32 * CL_BROW <= CL_WARP_SMEM, "byte rows must fit behind window buffer 0");
@@ -992,7 +993,9 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
         return t;
     };
     // dynamic units are dealt round-robin to the SM queues: the CTAs that share an SM (and its issue
-    // slots, which the warp arbiter does not hand out evenly) draw from the same counter
+    // slots, which the warp arbiter does not hand out evenly) draw from the same counter.  (Measured and
+    // dropped: a warp whose queue has run dry trying 3 / 8 other SMs' queues - 144.3 / 147.4 against
+    // 143.3 us/step: the failed attempts of the last warps cost more than the stolen units save.)
     auto fix = [&](int raw, int j) -> int { return j < rounds0 ? raw + u_lo : dyn_lo + ctx.q + ctx.nq * raw; };
     const int4 z4 = make_int4(0, 0, 0, 0);
     int u = fix(__shfl_sync(0xffffffffu, grab(0), 0), 0), un = fix(__shfl_sync(0xffffffffu, grab(1), 0), 1);
@@ -1305,7 +1308,14 @@ cells_persistent_kernel(const CellsArgs a) {
         if (!final) ctx.pr ^= 1;
         CL_PROF(0);
         if (final && a.blk > 0) __threadfence_system();      // the staged outputs live on peer GPUs
+        unsigned long long gt0 = 0;
+        if (ctx.pt && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
         CL_BARRIER();
+        if (ctx.pt && tid == 0) {                            // (debug) wall-clock ns of this CTA's arrival / exit
+            unsigned long long gt1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+            ctx.pt[9] = (long long)gt0; ctx.pt[10] = (long long)gt1;
+        }
         CL_PROF(1);
         if (a.P > 1 && final && a.blk > 0) (void)peer_sync(a, ctx, false);   // every rank's outputs have landed
         if (a.P > 1 && !final) {
@@ -1651,6 +1661,22 @@ int cells_run(ljmd_handle* h, const float2* R_in, const float2* V_in, float2* R_
             double mean = 0, mx = 0;
             for (int c = 0; c < cl->G; ++c) { mean += pv[c * 12 + k]; mx = std::max<double>(mx, (double)pv[c * 12 + k]); }
             fprintf(stderr, "[ljmd cells prof] %-16s mean %12.0f  max %12.0f clocks (launch total)\n", nm[k], mean / cl->G, mx);
+        }
+        {   // the last step barrier of the launch in wall-clock time: how long after the LAST arrival a CTA leaves
+            unsigned long long last_arr = 0, first_arr = ~0ull;
+            for (int c = 0; c < cl->G; ++c) {
+                last_arr = std::max<unsigned long long>(last_arr, (unsigned long long)pv[c * 12 + 9]);
+                first_arr = std::min<unsigned long long>(first_arr, (unsigned long long)pv[c * 12 + 9]);
+            }
+            double mean_exit = 0, max_exit = 0, mean_arr = 0;
+            for (int c = 0; c < cl->G; ++c) {
+                const double e = (double)((unsigned long long)pv[c * 12 + 10] - last_arr);
+                mean_exit += e; max_exit = std::max(max_exit, e);
+                mean_arr += (double)(last_arr - (unsigned long long)pv[c * 12 + 9]);
+            }
+            fprintf(stderr, "[ljmd cells prof] last step barrier: arrivals spread %.2f us (mean CTA waits %.2f us for the last one), "
+                            "exit %.2f us (mean) / %.2f us (max) after the last arrival\n",
+                    1e-3 * (double)(last_arr - first_arr), 1e-3 * mean_arr / cl->G, 1e-3 * mean_exit / cl->G, 1e-3 * max_exit);
         }
         if (getenv("LJMD_CELLS_PROF_CTAS")) {
             fprintf(stderr, "[ljmd cells prof] force+integrate clocks by CTA (launch total, /1000):");
