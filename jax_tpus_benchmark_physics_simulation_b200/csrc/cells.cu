@@ -123,7 +123,7 @@ struct CellsArgs {
     int*      mail;                 // = peer_mail[rank]
     int       nloc_of[LJMD_MAX_RANKS];       // owned rows of every rank
     float inv_hy, inv_wx, rlist2, half_skin2, dt;
-    float static_frac;              // share of a warp's units that is dealt statically (the rest: dynamic queue)
+    float static_frac;              // share of a warp's units that is dealt statically (the rest: dynamic queues)
     float2* R[2];
     float2* V[2];
     int*    orig[2];
@@ -995,7 +995,8 @@ __device__ __forceinline__ void warp_pass(const CellsArgs& a, const Ctx& ctx, co
     // dynamic units are dealt round-robin to the SM queues: the CTAs that share an SM (and its issue
     // slots, which the warp arbiter does not hand out evenly) draw from the same counter.  (Measured and
     // dropped: a warp whose queue has run dry trying 3 / 8 other SMs' queues - 144.3 / 147.4 against
-    // 143.3 us/step: the failed attempts of the last warps cost more than the stolen units save.)
+    // 143.3 us/step: the failed attempts of the last warps cost more than the stolen units save; keeping the
+    // last 3 - 20 % of the units in one global overflow queue - 142.1 ... 144.5 vs 142.9 us/step: no effect.)
     auto fix = [&](int raw, int j) -> int { return j < rounds0 ? raw + u_lo : dyn_lo + ctx.q + ctx.nq * raw; };
     const int4 z4 = make_int4(0, 0, 0, 0);
     int u = fix(__shfl_sync(0xffffffffu, grab(0), 0), 0), un = fix(__shfl_sync(0xffffffffu, grab(1), 0), 1);
@@ -1265,7 +1266,7 @@ cells_persistent_kernel(const CellsArgs a) {
         fl.s = s; fl.par = par; fl.kick1 = kick1; fl.final = final; fl.want_e = want_e; fl.want_pe = want_pe;
         fl.want_ke = want_ke; fl.thermo = thermo; fl.sample = sample;
         const int u_lo = ctx.own_s >> 5, u_hi = (ctx.own_e + 31) >> 5;      // 32-slot units
-        if (gtid < CL_QMAX) __stcg(&a.sched[(par ^ 1) * CL_QMAX + gtid], 0);   // the other parity's unit counters: idle this step
+        for (int k = gtid; k < CL_QMAX; k += gsz) __stcg(&a.sched[(par ^ 1) * CL_QMAX + k], 0);   // the other parity's unit counters: idle this step
         int moved = 0;
         if (want_pe)
             warp_pass<true, false>(a, ctx, fl, wp, moved);
