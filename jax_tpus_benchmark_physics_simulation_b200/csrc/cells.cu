@@ -49,7 +49,10 @@ namespace ljmd {
 
 namespace {
 
-constexpr int CL_B5 = 3;          // slots per thread per trip of the rebuild gather (B5)
+#ifndef CL_B5_
+#define CL_B5_ 3
+#endif
+constexpr int CL_B5 = CL_B5_;     // slots per thread per trip of the rebuild gather (B5)
 #ifndef CL_THREADS_
 #define CL_THREADS_ 512
 #endif
