@@ -74,6 +74,17 @@ FLOP_PER_UNORDERED_N3L = 33.0   # Newton's-third-law tiles: one evaluation (25) 
 BYTES_PER_PARTICLE_STEP = 32.0  # read+write R,V as float2
 
 
+def workload_config(wl_name, wl, world):
+    """The `config` object of the JSON line: the same for this arm and for --impl reference."""
+    N = wl["N"]
+    sharded = world > 1 and N >= SHARD_MIN_N
+    parallelism = "single GPU" if world == 1 else (f"sharded x{world}" if sharded else f"replicas x{world}")
+    return {"workload": wl_name, "desc": wl["desc"], "N": N, "rc": wl["rc"], "dt": wl["dt"],
+            "md_steps_per_step": wl["md_steps"], "path": wl["path"], "parallelism": parallelism,
+            "l2": "flushed (256 MiB write) between timed steps; inputs of the cell workloads "
+                  "(256 MiB+) are larger than L2"}
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -224,8 +235,10 @@ def run_reference(args, wl_name, wl):
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "strong" if N >= SHARD_MIN_N else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic lattice+jitter (seed 0, jitter 0.05, kT 1.0)",
-        "config": {"workload": wl_name, "desc": wl["desc"], "N": N, "rc": rc, "dt": dt,
-                   "md_steps_per_step": 1, "path": wl["path"]},
+        # the arm's own config (the workload as the B200 arm defines it); what one bench step of THIS arm
+        # covers is stated in cpu_baseline.sample: a bounded sample, normalised by the metric
+        "config": workload_config(wl_name, wl, args.gpus),
+        "sample_md_steps_per_step": 1,
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": _NCPU,
                          "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
@@ -593,11 +606,7 @@ def main():
             "ms_per_step": m["ms_per_step"], "higher_is_better": True,
             "scaling": "strong" if m["N"] >= SHARD_MIN_N else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic lattice+jitter (seed 0, jitter 0.05, kT 1.0)",
-            "config": {"workload": wl_name, "desc": m["desc"], "N": m["N"], "rc": m["rc"], "dt": m["dt"],
-                       "md_steps_per_step": m["md_steps_per_step"], "path": m["path"],
-                       "parallelism": m["parallelism"],
-                       "l2": "flushed (256 MiB write) between timed steps; inputs of the cell workloads "
-                             "(256 MiB+) are larger than L2"},
+            "config": workload_config(wl_name, dict(WORKLOADS[wl_name], md_steps=m["md_steps_per_step"]), env.world),
             "pair_interactions_per_s": m["pair_interactions_per_s"],
             "us_per_md_step": m["us_per_md_step"], "wall_s": m["wall_s"], "clocks": m["clocks"],
             "e2e": m["e2e"], "gpu_launches": m["gpu_launches"],
