@@ -1,4 +1,4 @@
-// cells.cu — sorted strip-cell / bitmask-Verlet-list path for large N (BASELINE configs 4-5).
+// cells.cu — sorted strip-cell / byte-Verlet-list path for large N (BASELINE configs 4-5).
 //
 // Not in the reference (it only has the dense O(N^2) form, MD:51): the pair arithmetic is the
 // same as the all-pairs path (subtract, exact min-image, unfused r2, r2 < rc^2), so on identical
@@ -10,11 +10,12 @@
 // of cell (r, b) lies in bins [b-K, b+K] of rows r-1, r, r+1, i.e. in THREE CONTIGUOUS SLOT RANGES
 // (42 candidates at rho 0.8, against 57 for square 3x3 cells).
 //
-// Neighbour list.  Because the candidates are contiguous, a particle's Verlet list is a few
-// (first slot, 32-bit mask) entries — normally one per stencil row, 24 bytes per particle instead of
-// 4 bytes per neighbour — built at a rebuild from the same fp32 r2 as the force loop.  The per-step
-// pass walks the set bits two at a time: two neighbours of one particle fill the two lanes of the
-// packed FP32x2 instructions.
+// Neighbour list.  A unit = 32 consecutive slots = one warp.  All neighbours of a unit lie in three
+// contiguous slot WINDOWS (<= 84 slots each), which the per-step pass stages in shared memory; a
+// particle's Verlet list is ONE BYTE per neighbour - its index in the staged windows - built at a
+// rebuild from the same fp32 r2 as the force loop.  The per-step pass walks the bytes four per word: two
+// neighbours of one particle fill the two lanes of the packed FP32x2 instructions.  Units that straddle
+// a row or touch the periodic edge keep (first slot, 32-bit mask) entries and gather from global memory.
 //
 // Data layout in HBM (all in slot order, permuted only at a rebuild):
 //   R[2]     float2  positions, ping-pong by step (the buffer being read is never written in a step)
