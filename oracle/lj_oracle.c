@@ -3,11 +3,13 @@
  * of the hot path of the reference script
  *     /root/reference/molecular_dynamics_jax_single-host_workload.py   (MD:<line>)
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures, and JAX is
- * not installable in this image, so this restatement cannot be checked
- * against outputs of the reference itself.  It is pinned instead by (i) agreement with an
- * independent torch-autodiff restatement (oracle/lj_oracle.py, the closest analogue of
- * jit(grad(total_energy_fn))) and (ii) analytic known-answer tests (tests/test_oracle.py).
+ * PARITY PIN: the reference ships no tests, golden vectors or fixtures, and JAX / XLA are not
+ * installable in this image, so this restatement cannot be checked against the
+ * reference running on JAX.  It is pinned (tests/test_reference_golden.py) to vectors produced by
+ * the reference's OWN SOURCE FILE executed unmodified on a torch facade of the jax API
+ * (tests/golden/jax_facade.py, make_reference_golden.py), to the independent torch-autodiff
+ * restatement (oracle/lj_oracle.py) and to analytic known answers (tests/test_oracle.py).  Not
+ * covered by that pin: XLA's own reduction order and pow lowering.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library.  The product (jax_tpus_benchmark_physics_simulation_b200/) never does.

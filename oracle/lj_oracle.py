@@ -7,10 +7,14 @@ using torch CPU tensors: ``torch.round`` is round-half-to-even like ``jnp.round`
 zero gradient through ``round`` and respects the double-``where``.  The
 dense autodiff force below is the closest available analogue of ``jit(grad(total_energy_fn))``.
 
-PARITY UNPINNED: the reference has no tests / golden vectors and JAX cannot be installed in
-this image, so neither this file nor oracle/lj_oracle.c can be checked against outputs of the
-reference itself.  They are pinned against each other and against analytic known answers
-(tests/test_oracle.py).
+PARITY PIN: the reference has no tests / golden vectors and JAX / XLA cannot be installed in this
+image, so neither this file nor oracle/lj_oracle.c can be checked against outputs of the reference
+running on JAX.  What they ARE pinned to (tests/test_reference_golden.py): vectors produced by the
+reference's OWN SOURCE FILE executed unmodified on a torch facade of the jax API
+(tests/golden/jax_facade.py, make_reference_golden.py -> tests/golden/ref_md_*.npz) - box size and
+periodic_displacement bit for bit, energy, autodiff forces, one step, equilibration, production with
+its sampling rule and dropped sample, g(r) - plus each other and analytic known answers
+(tests/test_oracle.py).  Not covered by that pin: XLA's own reduction order and pow lowering.
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module;
 the product package never does.

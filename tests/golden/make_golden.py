@@ -1,7 +1,8 @@
 """Writes tests/golden/lj_golden_n64.npz from the torch-autodiff restatement of the reference
-(oracle/lj_oracle.py).  The reference itself cannot be imported here (no JAX in the image), so
-these vectors pin the two independent restatements and the CUDA path to each other; they are
-NOT outputs of the reference.  Run:  python tests/golden/make_golden.py"""
+(oracle/lj_oracle.py).  These vectors pin the two independent restatements and the CUDA path to each
+other (incl. the cutoff variants the reference does not have); they are NOT outputs of the reference.
+Vectors made by the reference's own source file are tests/golden/ref_md_*.npz
+(make_reference_golden.py).  Run:  python tests/golden/make_golden.py"""
 import os
 import sys
 

@@ -1,7 +1,8 @@
 """CPU tests that pin the oracle (oracle/): the C restatement and the torch-autodiff
 restatement against each other and against analytic known answers.  The
 reference ships no golden vectors and JAX is not installable here, so parity with the
-reference itself is unpinned; these tests are the pin."""
+reference running on JAX cannot be; these tests and tests/test_reference_golden.py (vectors made by the
+reference's own source on a torch facade of jax) are the pin."""
 import math
 import os
 
