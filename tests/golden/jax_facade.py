@@ -100,7 +100,19 @@ def _make_jnp():
         c, e = np.histogram(x.detach().numpy().astype(np.float32), bins=bins.detach().numpy().astype(np.float32))
         return torch.from_numpy(c.astype(np.int64)), bins
     m.histogram = histogram
-    m.array = lambda x, dtype=None: _t(x)
+    def array(x, dtype=None):
+        if isinstance(x, (list, tuple)) and x and isinstance(x[0], torch.Tensor):
+            return torch.stack([_t(v) for v in x])
+        t = _t(x)
+        return t.to(F32) if t.dtype == torch.float64 else t
+    m.array = array
+    m.zeros_like = torch.zeros_like
+    m.arange = lambda n: torch.arange(n)
+    m.stack = lambda xs, axis=0: torch.stack([_t(v) for v in xs], dim=axis)
+    linalg = types.ModuleType("jax.numpy.linalg")
+    # jnp.linalg.norm of a vector: sqrt(sum(|x|^2)), correctly rounded sqrt (see sqrt above)
+    linalg.norm = lambda x: m.sqrt(torch.sum(x * x))
+    m.linalg = linalg
     return m
 
 
@@ -154,6 +166,11 @@ class _At:
         t = self.t
 
         class _Set:
+            def add(self, v):                      # acc.at[i].add(x)  (NBODY:64)
+                out = t.clone()
+                out[idx] = out[idx] + v
+                return out
+
             def set(self, v):
                 # out-of-range index: JAX drops the update (MD:95-100 relies on it)
                 n = t.shape[0]

@@ -70,3 +70,34 @@ def test_gpu_pair_accel_rejects_bad_arguments():
     lib = _lib.load()
     assert lib.ljmd_pair_accel(0, None, None, 4, 1.0, None, None) != 0
     assert lib.ljmd_pair_accel(7, None, None, 4, 1.0, None, None) != 0
+
+
+# ---- vectors from the reference's own function source (tests/golden/make_pairlaw_golden.py) -----------
+import os as _os
+
+_GOLD = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "ref_pairlaw.npz")
+_CASES = ["em3_ic", "n2", "n5", "n5_coincident"]
+
+
+@pytest.mark.parametrize("name", _CASES)
+def test_oracle_gravity_vs_reference_function_source(oracle, name):
+    g = np.load(_GOLD)
+    pos, mass, G = g[f"{name}_pos"], g[f"{name}_mass"], float(g["G"])
+    for law in ("nbody", "em3"):
+        ref = g[f"{name}_{law}"]
+        got = oracle.c_gravity(pos, mass, G, law)
+        assert np.isfinite(ref).all()
+        assert np.abs(got - ref).max() <= 2e-6 * max(np.abs(ref).max(), 1e-30)
+    assert np.abs(oracle.gravity_nbody_loops(pos, mass, G) - g[f"{name}_nbody"]).max() <= 2e-6 * np.abs(g[f"{name}_nbody"]).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", _CASES)
+def test_gpu_pair_accel_vs_reference_function_source(name):
+    from jax_tpus_benchmark_physics_simulation_b200.pairwise import pairwise_forces, gravity_acceleration
+    g = np.load(_GOLD)
+    pos, mass, G = g[f"{name}_pos"], g[f"{name}_mass"], float(g["G"])
+    a = pairwise_forces(pos, mass, G).numpy()
+    e = gravity_acceleration(pos, mass, G).numpy()
+    assert np.abs(a - g[f"{name}_nbody"]).max() <= 2e-6 * np.abs(g[f"{name}_nbody"]).max()
+    assert np.abs(e - g[f"{name}_em3"]).max() <= 2e-6 * np.abs(g[f"{name}_em3"]).max()
