@@ -40,6 +40,13 @@ constexpr int AP_THREADS = 128;   // 4 warps: one per SM sub-partition
 #ifndef AP_MINBLOCKS
 #define AP_MINBLOCKS 4
 #endif
+#ifndef AP_TB_UNROLL
+#define AP_TB_UNROLL 4
+#endif
+constexpr int kTileBothUnroll = AP_TB_UNROLL;
+#ifndef AP_TILE_BOTH
+#define AP_TILE_BOTH 1      // 1 = both halves of a 64 x 64 tile in one rotation loop (tile_both), 0 = one after the other
+#endif
 constexpr int kApUnroll = AP_UNROLL;   // j particles per unrolled inner-loop body
 constexpr int J_UNIT     = 8;     // granularity of the j split (particles)
 constexpr int TILE_J     = 512;   // j particles staged per shared-memory tile (8 KB)
@@ -235,6 +242,63 @@ __device__ __forceinline__ void tile_half(const PairConsts& pc, const PairConsts
     fjy = -ajy;
 }
 
+// Both halves of a 64 x 64 tile in ONE rotation loop: the two travelling j sets (h = 0: lanes' j, h = 1:
+// j + 32) are independent dependency chains (evaluate -> accumulate the reaction -> four shuffles), so
+// interleaving them doubles the instruction-level parallelism of a warp that shares its scheduler with
+// only three others (107 registers: 4 CTAs of 4 warps per SM).  Same arithmetic per pair as tile_half.
+template <bool CUTOFF, bool PE, bool N3L>
+__device__ __forceinline__ void tile_both(const PairConsts& pc, const PairConsts2& pc2, float2 xi2, float2 yi2,
+                                          float xja, float yja, float xjb, float yjb,
+                                          float2& fx2, float2& fy2, float2& pe2,
+                                          float& fjxa, float& fjya, float& fjxb, float& fjyb) {
+    const int src = (threadIdx.x + 1) & 31;
+    float aax = 0.0f, aay = 0.0f, abx = 0.0f, aby = 0.0f;
+    float2 gx2 = make_float2(0.0f, 0.0f), gy2 = gx2;       // second accumulator pair (half b)
+    {   // step 0 peeled: the only step at which j can be one of this lane's own i (diagonal tiles):
+        // half a meets i0 (self0), half b meets i1 (self1)
+        float2 fa, dxa, dya, fb, dxb, dyb;
+        if (N3L) {
+            pair2_eval<CUTOFF, PE, false>(xi2, yi2, xja, yja, true, true, pc, pc2, fa, dxa, dya, pe2);
+            pair2_eval<CUTOFF, PE, false>(xi2, yi2, xjb, yjb, true, true, pc, pc2, fb, dxb, dyb, pe2);
+        } else {
+            pair2_eval<CUTOFF, PE, true>(xi2, yi2, xja, yja, false, true, pc, pc2, fa, dxa, dya, pe2);
+            pair2_eval<CUTOFF, PE, true>(xi2, yi2, xjb, yjb, true, false, pc, pc2, fb, dxb, dyb, pe2);
+        }
+        fx2 = __ffma2_rn(fa, dxa, fx2); fy2 = __ffma2_rn(fa, dya, fy2);
+        gx2 = __ffma2_rn(fb, dxb, gx2); gy2 = __ffma2_rn(fb, dyb, gy2);
+        if (N3L) {
+            aax = fmaf(fa.y, dxa.y, __fmul_rn(fa.x, dxa.x)); aay = fmaf(fa.y, dya.y, __fmul_rn(fa.x, dya.x));
+            abx = fmaf(fb.y, dxb.y, __fmul_rn(fb.x, dxb.x)); aby = fmaf(fb.y, dyb.y, __fmul_rn(fb.x, dyb.x));
+        }
+        xja = __shfl_sync(0xffffffffu, xja, src); yja = __shfl_sync(0xffffffffu, yja, src);
+        xjb = __shfl_sync(0xffffffffu, xjb, src); yjb = __shfl_sync(0xffffffffu, yjb, src);
+        if (N3L) {
+            aax = __shfl_sync(0xffffffffu, aax, src); aay = __shfl_sync(0xffffffffu, aay, src);
+            abx = __shfl_sync(0xffffffffu, abx, src); aby = __shfl_sync(0xffffffffu, aby, src);
+        }
+    }
+#pragma unroll kTileBothUnroll
+    for (int s = 1; s < 32; ++s) {
+        float2 fa, dxa, dya, fb, dxb, dyb;
+        pair2_eval<CUTOFF, PE, false>(xi2, yi2, xja, yja, true, true, pc, pc2, fa, dxa, dya, pe2);
+        pair2_eval<CUTOFF, PE, false>(xi2, yi2, xjb, yjb, true, true, pc, pc2, fb, dxb, dyb, pe2);
+        fx2 = __ffma2_rn(fa, dxa, fx2); fy2 = __ffma2_rn(fa, dya, fy2);
+        gx2 = __ffma2_rn(fb, dxb, gx2); gy2 = __ffma2_rn(fb, dyb, gy2);
+        if (N3L) {
+            aax = fmaf(fa.y, dxa.y, fmaf(fa.x, dxa.x, aax)); aay = fmaf(fa.y, dya.y, fmaf(fa.x, dya.x, aay));
+            abx = fmaf(fb.y, dxb.y, fmaf(fb.x, dxb.x, abx)); aby = fmaf(fb.y, dyb.y, fmaf(fb.x, dyb.x, aby));
+        }
+        xja = __shfl_sync(0xffffffffu, xja, src); yja = __shfl_sync(0xffffffffu, yja, src);
+        xjb = __shfl_sync(0xffffffffu, xjb, src); yjb = __shfl_sync(0xffffffffu, yjb, src);
+        if (N3L) {
+            aax = __shfl_sync(0xffffffffu, aax, src); aay = __shfl_sync(0xffffffffu, aay, src);
+            abx = __shfl_sync(0xffffffffu, abx, src); aby = __shfl_sync(0xffffffffu, aby, src);
+        }
+    }
+    fx2.x += gx2.x; fx2.y += gx2.y; fy2.x += gy2.x; fy2.y += gy2.y;
+    fjxa = -aax; fjya = -aay; fjxb = -abx; fjyb = -aby;
+}
+
 __device__ __forceinline__ float2 ld_pos(const float2* __restrict__ R, int j, int N, float sent) {
     return (j < N) ? __ldcg(&R[j]) : make_float2(sent, sent);
 }
@@ -276,6 +340,26 @@ __device__ __forceinline__ void ap3_phase_forces(const ApArgs& a, const float2* 
                 if (ba > bb) continue;                          // lower triangle (diagonal patches only)
                 float2 pe2 = make_float2(0.0f, 0.0f);
                 float2 tfx = make_float2(0.0f, 0.0f), tfy = tfx;   // per-tile sums (bounded chains)
+#if AP_TILE_BOTH
+                {
+                    const int ja = bb * T3_BLK + lane, jb = ja + 32;
+                    const float2 pa = ld_pos(Rcur, ja, a.N, SENT_J), pb = ld_pos(Rcur, jb, a.N, SENT_J);
+                    float fjxa, fjya, fjxb, fjyb;
+                    if (ba < bb) {
+                        tile_both<CUTOFF, PE, true>(pc, pc2, xi2, yi2, pa.x, pa.y, pb.x, pb.y, tfx, tfy, pe2,
+                                                    fjxa, fjya, fjxb, fjyb);
+                        float2 acc = colacc[cc * T3_BLK + lane];
+                        acc.x += fjxa; acc.y += fjya;
+                        colacc[cc * T3_BLK + lane] = acc;
+                        acc = colacc[cc * T3_BLK + 32 + lane];
+                        acc.x += fjxb; acc.y += fjyb;
+                        colacc[cc * T3_BLK + 32 + lane] = acc;
+                    } else {
+                        tile_both<CUTOFF, PE, false>(pc, pc2, xi2, yi2, pa.x, pa.y, pb.x, pb.y, tfx, tfy, pe2,
+                                                     fjxa, fjya, fjxb, fjyb);
+                    }
+                }
+#else
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
                     const int j = bb * T3_BLK + h * 32 + lane;
@@ -290,6 +374,7 @@ __device__ __forceinline__ void ap3_phase_forces(const ApArgs& a, const float2* 
                         tile_half<CUTOFF, PE, false>(pc, pc2, xi2, yi2, pj.x, pj.y, h == 0, h == 1, tfx, tfy, pe2, fjx, fjy);
                     }
                 }
+#endif
                 fx2.x += tfx.x; fx2.y += tfx.y; fy2.x += tfy.x; fy2.y += tfy.y;
                 // energy bookkeeping in the ORDERED-pair convention of the caller (0.5 * sum):
                 // an unordered pair of an off-diagonal tile counts twice, a diagonal tile is ordered
